@@ -1,0 +1,114 @@
+"""
+Deterministic synthetic designs in the reference's on-disk formats.
+
+The reference ships no data (examples/EmulatorTraining.ipynb reads ../data/*.pkl which are not
+in the repository), so every test / bench fixture is produced here:
+
+  * training pickle  {str(id): {"parameter": [p], "obs": [2, m]}}   (src/emulator.py:378-415)
+  * experiment pickle, same layout with one entry                    (src/mcmc.py:302-324)
+  * parameter file   "name: label, min, max"                         (src/__init__.py:21-32)
+
+The recipe (box, Latin-hypercube design, tanh-network simulator) is the one SURVEY.md 8d states.
+"""
+import os
+import pickle
+
+import numpy as np
+from scipy.stats import qmc
+
+# BASELINE.json configs: (p params, n design points, m observables, q principal components)
+SHAPES = {
+    "C1": dict(p=5, n=100, m=50, q=10),
+    "C2": dict(p=17, n=500, m=300, q=20),
+    "C3": dict(p=15, n=1000, m=300, q=20),
+}
+
+
+def box(p):
+    lo = np.zeros(p)
+    hi = 1.0 + 0.25 * np.arange(p)
+    return lo, hi
+
+
+class Simulator:
+    """Y = 5 + tanh(2 U W1) W2 + 0.5 sin(3 U_0) linspace(0,1,m),  U = (x-lo)/(hi-lo)."""
+
+    def __init__(self, p, m, seed=20261018, hidden=24):
+        rng = np.random.default_rng(seed)
+        self.p, self.m = p, m
+        self.lo, self.hi = box(p)
+        self.W1 = rng.normal(0.0, np.sqrt(1.0 / p), (p, hidden))
+        self.W2 = rng.normal(0.0, np.sqrt(1.0 / hidden), (hidden, m))
+        self.ramp = np.linspace(0.0, 1.0, m)
+
+    def unit(self, X):
+        return (np.asarray(X, dtype=np.float64) - self.lo) / (self.hi - self.lo)
+
+    def __call__(self, X):
+        U = np.atleast_2d(self.unit(X))
+        H = np.tanh(2.0 * U @ self.W1)
+        return 5.0 + H @ self.W2 + 0.5 * np.sin(3.0 * U[:, :1]) * self.ramp
+
+
+def design(p, n, seed=7):
+    lo, hi = box(p)
+    return lo + (hi - lo) * qmc.LatinHypercube(d=p, seed=seed).random(n)
+
+
+def training_dict(p, n, m, noise=0.01, seed=11):
+    sim = Simulator(p, m)
+    Xtr = design(p, n)
+    rng = np.random.default_rng(seed)
+    Y = sim(Xtr) + noise * rng.standard_normal((n, m))
+    return {str(i): {"parameter": Xtr[i].copy(),
+                     "obs": np.stack([Y[i], np.full(m, noise)])} for i in range(n)}
+
+
+def experiment_dict(p, m, rel_err=0.03, u0=0.4):
+    sim = Simulator(p, m)
+    x0 = sim.lo + u0 * (sim.hi - sim.lo)
+    y = sim(x0)[0]
+    return {"0": {"parameter": x0, "obs": np.stack([y, rel_err * np.abs(y)])}}
+
+
+def parameter_file_text(p):
+    lo, hi = box(p)
+    lines = ["# synthetic design box", "# format: parameter_name: label, min, max"]
+    for d in range(p):
+        lines.append("par%d: $\\theta_{%d}$, %r, %r" % (d, d, float(lo[d]), float(hi[d])))
+    return "\n".join(lines) + "\n"
+
+
+def write_fixture(outdir, p, n, m, tag=""):
+    """Write train/exp pickles + parameter file; returns their paths."""
+    os.makedirs(outdir, exist_ok=True)
+    paths = dict(train=os.path.join(outdir, "train%s.pkl" % tag),
+                 exp=os.path.join(outdir, "exp%s.pkl" % tag),
+                 par=os.path.join(outdir, "par%s.txt" % tag))
+    with open(paths["train"], "wb") as f:
+        pickle.dump(training_dict(p, n, m), f)
+    with open(paths["exp"], "wb") as f:
+        pickle.dump(experiment_dict(p, m), f)
+    with open(paths["par"], "w") as f:
+        f.write(parameter_file_text(p))
+    return paths
+
+
+def walkers(p, N, seed=3, frac_outside=0.01):
+    """Uniform walkers in the box with a fixed fraction of rows pushed out of bounds."""
+    lo, hi = box(p)
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(lo, hi, (N, p))
+    n_out = int(round(frac_outside * N))
+    if n_out:
+        rows = rng.choice(N, n_out, replace=False)
+        cols = rng.integers(0, p, n_out)
+        X[rows, cols] = hi[cols] + 0.1
+    return X
+
+
+def systematic_cov(m, rank=5, scale=0.02, seed=5):
+    """Random PSD low-rank 'systematic' term for the full-covariance sweep (BASELINE config 4)."""
+    rng = np.random.default_rng(seed)
+    G = scale * rng.standard_normal((m, rank))
+    return G @ G.T
