@@ -1,0 +1,63 @@
+"""ctypes binding of libgpbt_b200.so (C ABI: include/gpbt.h).
+
+There is deliberately no fallback: if the CUDA library has not been built, importing this module
+raises, and every product entry point that needs the GPU fails loudly."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgpbt_b200.so")
+
+KERNEL_RBF, KERNEL_MATERN32 = 0, 1
+FLAG_NO_PCA, FLAG_EXP_DIAG = 1, 2
+PATH_AUTO, PATH_DENSE, PATH_LOWRANK = 0, 1, 2
+
+# every symbol include/gpbt.h declares (tests/test_cabi.py checks the library exports them all)
+SYMBOLS = [
+    "gpbt_last_error", "gpbt_version", "gpbt_emulator_create", "gpbt_emulator_destroy",
+    "gpbt_pc_predict", "gpbt_backtransform", "gpbt_mvn_loglike", "gpbt_chain_create",
+    "gpbt_chain_destroy", "gpbt_chain_predict", "gpbt_log_posterior", "gpbt_log_posterior_host",
+    "gpbt_chain_workspace_bytes", "gpbt_launch_count",
+]
+
+
+class GpbtError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU implementation to fall back to." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    dp, vp, i64, i32, dbl = C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_double
+    lib.gpbt_last_error.restype = C.c_char_p
+    lib.gpbt_version.restype = i32
+    lib.gpbt_launch_count.restype = i64
+    lib.gpbt_emulator_create.argtypes = [C.POINTER(vp), i32, i32, i32, i32, i32, i32] + [dp] * 10
+    lib.gpbt_emulator_destroy.argtypes = [vp]
+    lib.gpbt_pc_predict.argtypes = [vp, dp, dp, dp, dp, i64, i64, vp]
+    lib.gpbt_backtransform.argtypes = [vp, dp, dp, i64, dp, i64, dp, i64, i64, i64, vp]
+    lib.gpbt_mvn_loglike.argtypes = [dp, dp, dp, dp, dp, dp, dbl, i64, i32, vp]
+    lib.gpbt_chain_create.argtypes = [C.POINTER(vp), C.POINTER(vp), i32, i32, dp, dp, dp, dp, dp, dp, dbl, dbl]
+    lib.gpbt_chain_destroy.argtypes = [vp]
+    lib.gpbt_chain_predict.argtypes = [vp, dp, dbl, dp, dp, i64, vp]
+    lib.gpbt_log_posterior.argtypes = [vp, dp, dbl, dp, dp, i64, i32, vp]
+    lib.gpbt_log_posterior_host.argtypes = [vp, dp, dbl, dp, dp, i64, i32]
+    lib.gpbt_chain_workspace_bytes.argtypes = [vp]
+    lib.gpbt_chain_workspace_bytes.restype = i64
+    return lib
+
+
+lib = _load()
+
+
+def check(rc):
+    if rc != 0:
+        raise GpbtError("gpbt error %d: %s" % (rc, lib.gpbt_last_error().decode()))
+
+
+def host_ptr(a):
+    """pointer to a C-contiguous float64 numpy array (None -> NULL)"""
+    return None if a is None else a.ctypes.data_as(C.c_void_p)

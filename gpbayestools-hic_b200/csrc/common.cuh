@@ -1,0 +1,34 @@
+// Shared device helpers for the gpbt kernels (sm_100a, FP64 throughout).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gpbt {
+
+constexpr int kWarp = 32;
+
+// D(8x8) += A(8x4, row) * B(4x8, col), FP64.  On sm_100a this is the only FP64 tensor shape the
+// hardware has (the m16n8k{4,8,16} PTX shapes are lowered to several DMMA.8x8x4 by ptxas).
+// Fragment ownership for lane l:  A[l/4][l%4],  B[l%4][l/4],  C[l/4][2*(l%4) + {0,1}].
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1},{%2},{%3},{%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// 16-byte read-only load of two doubles (immutable state only: Linv, Xs, A ...)
+__device__ __forceinline__ double2 ldg2(const double* p) {
+  return __ldg(reinterpret_cast<const double2*>(p));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__host__ __device__ __forceinline__ int64_t round_up(int64_t x, int64_t a) {
+  return (x + a - 1) / a * a;
+}
+
+}  // namespace gpbt

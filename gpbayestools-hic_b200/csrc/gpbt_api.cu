@@ -1,0 +1,523 @@
+// C ABI of libgpbt_b200.so (declared in include/gpbt.h): handle management, state upload with the
+// padding the kernels want, launch configuration and the host-buffer convenience entry point.
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/gpbt.h"
+#include "backtransform.cuh"
+#include "chol_loglike.cuh"
+#include "common.cuh"
+#include "lowrank_loglike.cuh"
+#include "pc_predict.cuh"
+
+using namespace gpbt;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(x)                                                                                   \
+  do {                                                                                          \
+    cudaError_t e_ = (x);                                                                       \
+    if (e_ != cudaSuccess)                                                                      \
+      return fail((int)e_, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+#define LAUNCH_CHECK()                                                                  \
+  do {                                                                                  \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                 \
+    cudaError_t e_ = cudaGetLastError();                                                \
+    if (e_ != cudaSuccess)                                                              \
+      return fail((int)e_, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+// 2*log(0 + 1e-16) - 0/scale: the extra_std prior term of the reference with extra_std == 0
+// (src/mcmc.py:199, 281, 296-297)
+const double kSysConst = 2.0 * std::log(0.0 + 1e-16);
+
+template <typename T>
+int upload(T** dst, const std::vector<T>& v) {
+  CU(cudaMalloc(dst, std::max<size_t>(v.size(), 1) * sizeof(T)));
+  if (!v.empty()) CU(cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int max_optin_smem() {
+  int dev = 0, v = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  return v;
+}
+
+}  // namespace
+
+struct gpbt_emulator {
+  int p, p_pad, n, n_pad, q, q_pad, m, m_ld, kind, flags, device;
+  double *Xs, *ell, *c, *sn, *alpha, *W, *A, *mu, *scale, *Ctrunc;
+};
+
+struct gpbt_chain {
+  std::vector<gpbt_emulator_t> emus;
+  std::vector<int> q_off, m_off;
+  int p, Q, M, device;
+  bool has_lowrank;
+  double s_perp, logdetF_half;
+  double *lo, *hi, *y_exp, *cov_exp, *R, *c0;
+  // workspaces (grown on demand)
+  int64_t cap_rows = 0, cap_dense = 0, cap_x = 0;
+  double *z_mean = nullptr, *z_var = nullptr, *extra = nullptr, *mean = nullptr, *cov = nullptr;
+  double *x_dev = nullptr, *lp_dev = nullptr;
+  unsigned char* skip = nullptr;
+  int* notpd_dev = nullptr;
+  cudaStream_t stream = nullptr;
+  int64_t ws_bytes = 0;
+};
+
+extern "C" const char* gpbt_last_error(void) { return g_err.c_str(); }
+extern "C" int gpbt_version(void) { return 100; }
+extern "C" int64_t gpbt_launch_count(void) { return g_launches.load(); }
+
+// ------------------------------------------------------------------------------------------------
+// emulator state
+// ------------------------------------------------------------------------------------------------
+extern "C" int gpbt_emulator_create(gpbt_emulator_t* out, int p, int n, int q, int m, int kernel_kind,
+                                    int flags, const double* Xtr, const double* ell, const double* c,
+                                    const double* sn, const double* alpha, const double* Linv,
+                                    const double* A, const double* mu, const double* scale,
+                                    const double* Ctrunc) {
+  if (!out || p <= 0 || n <= 0 || q <= 0 || m <= 0 || !Xtr || !ell || !c || !sn || !alpha || !Linv || !mu)
+    return fail(GPBT_EINVAL, "gpbt_emulator_create: null or non-positive argument");
+  if (kernel_kind != GPBT_KERNEL_RBF && kernel_kind != GPBT_KERNEL_MATERN32)
+    return fail(GPBT_EINVAL, "gpbt_emulator_create: unknown kernel kind %d", kernel_kind);
+  const bool no_pca = flags & GPBT_FLAG_NO_PCA;
+  if (no_pca && (q != m || !scale)) return fail(GPBT_EINVAL, "no-PCA mode needs q == m and scale");
+  if (!no_pca && (!A || !Ctrunc)) return fail(GPBT_EINVAL, "PCA mode needs A and Ctrunc");
+
+  gpbt_emulator* e = new gpbt_emulator();
+  memset(e, 0, sizeof *e);
+  e->p = p; e->n = n; e->q = q; e->m = m; e->kind = kernel_kind; e->flags = flags;
+  e->p_pad = (int)round_up(p, 2);
+  e->n_pad = (int)round_up(n, 32);
+  e->q_pad = (int)round_up(q, 4);
+  e->m_ld = m;
+  while (e->m_ld % 8 != 4) e->m_ld++;  // conflict-free fragment loads in backtransform_cov_kernel
+  cudaGetDevice(&e->device);
+  const int P = e->p_pad, NP = e->n_pad;
+
+  std::vector<double> h;
+  h.assign((size_t)q * NP * P, 0.0);
+  for (int j = 0; j < q; j++)
+    for (int i = 0; i < n; i++)
+      for (int d = 0; d < p; d++)
+        h[((size_t)j * NP + i) * P + d] = Xtr[(size_t)i * p + d] / ell[(size_t)j * p + d];
+  if (int r = upload(&e->Xs, h)) return r;
+  h.assign((size_t)q * P, 1.0);
+  for (int j = 0; j < q; j++)
+    for (int d = 0; d < p; d++) h[(size_t)j * P + d] = ell[(size_t)j * p + d];
+  if (int r = upload(&e->ell, h)) return r;
+  h.assign(c, c + q);
+  if (int r = upload(&e->c, h)) return r;
+  h.assign(sn, sn + q);
+  if (int r = upload(&e->sn, h)) return r;
+  h.assign((size_t)q * NP, 0.0);
+  for (int j = 0; j < q; j++) memcpy(&h[(size_t)j * NP], alpha + (size_t)j * n, n * sizeof(double));
+  if (int r = upload(&e->alpha, h)) return r;
+  h.assign((size_t)q * NP * NP, 0.0);
+  for (int j = 0; j < q; j++)
+    for (int i = 0; i < n; i++)
+      memcpy(&h[((size_t)j * NP + i) * NP], Linv + ((size_t)j * n + i) * n, (size_t)(i + 1) * sizeof(double));
+  if (int r = upload(&e->W, h)) return r;
+  h.assign(mu, mu + m);
+  if (int r = upload(&e->mu, h)) return r;
+  if (scale) {
+    h.assign(scale, scale + m);
+    if (int r = upload(&e->scale, h)) return r;
+  }
+  if (!no_pca) {
+    h.assign((size_t)e->q_pad * e->m_ld, 0.0);
+    for (int k = 0; k < q; k++) memcpy(&h[(size_t)k * e->m_ld], A + (size_t)k * m, m * sizeof(double));
+    if (int r = upload(&e->A, h)) return r;
+    h.assign(Ctrunc, Ctrunc + (size_t)m * m);
+    if (int r = upload(&e->Ctrunc, h)) return r;
+  }
+  *out = e;
+  return 0;
+}
+
+extern "C" int gpbt_emulator_destroy(gpbt_emulator_t e) {
+  if (!e) return 0;
+  double* ptrs[] = {e->Xs, e->ell, e->c, e->sn, e->alpha, e->W, e->A, e->mu, e->scale, e->Ctrunc};
+  for (double* p : ptrs)
+    if (p) cudaFree(p);
+  delete e;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel (a)
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+template <int TW, int KIND>
+int launch_pc_predict(const PcPredictParams& prm, cudaStream_t st) {
+  const size_t smem = pc_predict_smem_bytes<TW>(prm.n_pad, prm.p_pad);
+  static size_t configured = 0;
+  if (smem > configured) {
+    CU(cudaFuncSetAttribute(pc_predict_kernel<TW, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  dim3 grid((unsigned)((prm.N + TW - 1) / TW), (unsigned)prm.q);
+  pc_predict_kernel<TW, KIND><<<grid, kPcThreads, smem, st>>>(prm);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+template <int KIND>
+int dispatch_pc_predict(const PcPredictParams& prm, cudaStream_t st) {
+  const size_t limit = (size_t)max_optin_smem();
+  // widest walker tile that fits in shared memory, narrowed while the grid would leave SMs idle
+  int tw = 32;
+  if (pc_predict_smem_bytes<32>(prm.n_pad, prm.p_pad) > limit) tw = 16;
+  if (tw == 16 && pc_predict_smem_bytes<16>(prm.n_pad, prm.p_pad) > limit) tw = 8;
+  if (tw == 8 && pc_predict_smem_bytes<8>(prm.n_pad, prm.p_pad) > limit)
+    return fail(GPBT_ESHAPE, "pc_predict: n = %d design points do not fit in shared memory", prm.n);
+  const int64_t want = 2 * 148;
+  while (tw > 8 && ((prm.N + tw - 1) / tw) * prm.q < want) tw >>= 1;
+  if (tw == 32) return launch_pc_predict<32, KIND>(prm, st);
+  if (tw == 16) return launch_pc_predict<16, KIND>(prm, st);
+  return launch_pc_predict<8, KIND>(prm, st);
+}
+
+int run_pc_predict(gpbt_emulator_t e, const double* X, const double* extra, double* zm, double* zv,
+                   int64_t ldz, int64_t N, cudaStream_t st) {
+  if (N <= 0) return 0;
+  PcPredictParams prm;
+  prm.X = X; prm.extra = extra; prm.Xs = e->Xs; prm.ell = e->ell; prm.c = e->c; prm.sn = e->sn;
+  prm.alpha = e->alpha; prm.W = e->W; prm.z_mean = zm; prm.z_var = zv; prm.ldz = ldz; prm.N = N;
+  prm.p = e->p; prm.p_pad = e->p_pad; prm.n = e->n; prm.n_pad = e->n_pad; prm.q = e->q;
+  return e->kind == GPBT_KERNEL_RBF ? dispatch_pc_predict<0>(prm, st) : dispatch_pc_predict<1>(prm, st);
+}
+
+int run_backtransform(gpbt_emulator_t e, const double* zm, const double* zv, int64_t ldz, double* mean,
+                      int64_t ld_mean, double* cov, int64_t ld_cov, int64_t col_off, int64_t N,
+                      cudaStream_t st) {
+  if (N <= 0) return 0;
+  BacktransformParams prm;
+  prm.z_mean = zm; prm.z_var = zv; prm.A = e->A; prm.mu = e->mu; prm.scale = e->scale;
+  prm.Ctrunc = e->Ctrunc; prm.mean = mean; prm.cov = cov; prm.ldz = ldz; prm.ld_mean = ld_mean;
+  prm.ld_cov = ld_cov; prm.col_off = col_off; prm.N = N; prm.q = e->q; prm.m = e->m; prm.m_ld = e->m_ld;
+  prm.flags = e->flags;
+  backtransform_mean_kernel<<<(unsigned)N, 128, 2 * e->q * sizeof(double), st>>>(prm);
+  LAUNCH_CHECK();
+  const bool diag = e->flags & (GPBT_FLAG_NO_PCA | GPBT_FLAG_EXP_DIAG);
+  if (cov != nullptr && !diag) {
+    const size_t smem = backtransform_smem_bytes(e->q_pad, e->m_ld);
+    if (smem > (size_t)max_optin_smem())
+      return fail(GPBT_ESHAPE, "backtransform: q*m = %d*%d does not fit in shared memory", e->q, e->m);
+    static size_t configured = 0;
+    if (smem > configured) {
+      CU(cudaFuncSetAttribute(backtransform_cov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    dim3 grid((unsigned)((e->m + kBtRows - 1) / kBtRows), (unsigned)N);
+    if (N > 65535) return fail(GPBT_ESHAPE, "backtransform: chunk the walkers (N = %lld > 65535)", (long long)N);
+    backtransform_cov_kernel<<<grid, kBtThreads, smem, st>>>(prm, e->q_pad);
+    LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+int run_chol(const double* mean, const double* y_exp, double* cov, const double* cov_add, double* lp,
+             int* n_notpd, const unsigned char* skip, double notpd_value, double add_const, int64_t N, int m,
+             cudaStream_t st) {
+  if (N <= 0) return 0;
+  const size_t smem = chol_smem_bytes(m);
+  if (smem > (size_t)max_optin_smem())
+    return fail(GPBT_ESHAPE, "mvn_loglike: m = %d observables exceed the shared-memory panel", m);
+  static size_t configured = 0;
+  if (smem > configured) {
+    CU(cudaFuncSetAttribute(chol_loglike_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  CholParams prm;
+  prm.mean = mean; prm.y_exp = y_exp; prm.cov = cov; prm.cov_add = cov_add; prm.lp = lp;
+  prm.n_notpd = n_notpd; prm.skip = skip; prm.notpd_value = notpd_value; prm.add_const = add_const;
+  prm.N = N; prm.m = m;
+  chol_loglike_kernel<<<(unsigned)N, kChThreads, smem, st>>>(prm);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// bounds mask for the dense path: skip[w] = outside, lp[w] = oob_value there
+__global__ void bounds_mask_kernel(const double* __restrict__ X, const double* __restrict__ lo,
+                                   const double* __restrict__ hi, int p, int64_t N, double oob,
+                                   unsigned char* __restrict__ skip, double* __restrict__ lp) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= N) return;
+  bool ok = true;
+  for (int d = 0; d < p; d++) {
+    const double x = X[w * p + d];
+    ok = ok && (x > lo[d]) && (x < hi[d]);
+  }
+  skip[w] = ok ? 0 : 1;
+  if (!ok) lp[w] = oob;
+}
+
+// extra_std_arr = extra_std * X[:, -1]   (src/mcmc.py:157)
+__global__ void extra_std_kernel(const double* __restrict__ X, int p, int64_t N, double scale,
+                                 double* __restrict__ out) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w < N) out[w] = scale * X[w * p + p - 1];
+}
+
+}  // namespace
+
+extern "C" int gpbt_pc_predict(gpbt_emulator_t emu, const double* X, const double* extra, double* zm,
+                               double* zv, int64_t ldz, int64_t N, void* stream) {
+  if (!emu || !X || !zm || !zv || ldz < emu->q || N < 0) return fail(GPBT_EINVAL, "gpbt_pc_predict: bad argument");
+  return run_pc_predict(emu, X, extra, zm, zv, ldz, N, (cudaStream_t)stream);
+}
+
+extern "C" int gpbt_backtransform(gpbt_emulator_t emu, const double* zm, const double* zv, int64_t ldz,
+                                  double* mean, int64_t ld_mean, double* cov, int64_t ld_cov,
+                                  int64_t col_off, int64_t N, void* stream) {
+  if (!emu || !zm || !zv || !mean || N < 0 || ld_mean < col_off + emu->m || (cov && ld_cov < col_off + emu->m))
+    return fail(GPBT_EINVAL, "gpbt_backtransform: bad argument");
+  // the covariance kernel's grid.y carries the walker index: chunk it
+  const int64_t step = 32768;
+  for (int64_t s = 0; s < N; s += step) {
+    const int64_t nn = std::min(step, N - s);
+    int r = run_backtransform(emu, zm + s * ldz, zv + s * ldz, ldz, mean + s * ld_mean, ld_mean,
+                              cov ? cov + (size_t)s * ld_cov * ld_cov : nullptr, ld_cov, col_off, nn,
+                              (cudaStream_t)stream);
+    if (r) return r;
+  }
+  return 0;
+}
+
+extern "C" int gpbt_mvn_loglike(const double* mean, const double* y_exp, double* cov, const double* cov_add,
+                                double* lp, int* n_notpd, double notpd_value, int64_t N, int m, void* stream) {
+  if (!mean || !cov || !lp || N < 0 || m <= 0) return fail(GPBT_EINVAL, "gpbt_mvn_loglike: bad argument");
+  return run_chol(mean, y_exp, cov, cov_add, lp, n_notpd, nullptr, notpd_value, 0.0, N, m, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// chain
+// ------------------------------------------------------------------------------------------------
+extern "C" int gpbt_chain_create(gpbt_chain_t* out, const gpbt_emulator_t* emus, int n_emu, int p,
+                                 const double* lo, const double* hi, const double* y_exp,
+                                 const double* cov_exp, const double* R, const double* c0, double s_perp,
+                                 double logdetF_half) {
+  if (!out || !emus || n_emu <= 0 || !lo || !hi || !y_exp || !cov_exp)
+    return fail(GPBT_EINVAL, "gpbt_chain_create: null argument");
+  gpbt_chain* ch = new gpbt_chain();
+  ch->p = p; ch->Q = 0; ch->M = 0;
+  cudaGetDevice(&ch->device);
+  bool all_pca = true;
+  for (int i = 0; i < n_emu; i++) {
+    if (!emus[i] || emus[i]->p != p) { delete ch; return fail(GPBT_EINVAL, "emulator %d: parameter count mismatch", i); }
+    ch->emus.push_back(emus[i]);
+    ch->q_off.push_back(ch->Q);
+    ch->m_off.push_back(ch->M);
+    ch->Q += emus[i]->q;
+    ch->M += emus[i]->m;
+    if (emus[i]->flags & (GPBT_FLAG_NO_PCA | GPBT_FLAG_EXP_DIAG)) all_pca = false;
+  }
+  if (R && !all_pca) { delete ch; return fail(GPBT_ENOTAPPLICABLE, "low-rank factors given for a chain with a no-PCA / exp-diag emulator"); }
+  if (R && !c0) { delete ch; return fail(GPBT_EINVAL, "R given without c0"); }
+  ch->has_lowrank = R != nullptr;
+  ch->s_perp = s_perp; ch->logdetF_half = logdetF_half;
+  std::vector<double> h;
+  h.assign(lo, lo + p); if (int r = upload(&ch->lo, h)) return r;
+  h.assign(hi, hi + p); if (int r = upload(&ch->hi, h)) return r;
+  h.assign(y_exp, y_exp + ch->M); if (int r = upload(&ch->y_exp, h)) return r;
+  h.assign(cov_exp, cov_exp + (size_t)ch->M * ch->M); if (int r = upload(&ch->cov_exp, h)) return r;
+  ch->R = nullptr; ch->c0 = nullptr;
+  if (R) {
+    h.assign(R, R + (size_t)ch->Q * ch->Q); if (int r = upload(&ch->R, h)) return r;
+    h.assign(c0, c0 + ch->Q); if (int r = upload(&ch->c0, h)) return r;
+  }
+  CU(cudaMalloc(&ch->notpd_dev, sizeof(int)));
+  CU(cudaStreamCreateWithFlags(&ch->stream, cudaStreamNonBlocking));
+  *out = ch;
+  return 0;
+}
+
+extern "C" int gpbt_chain_destroy(gpbt_chain_t ch) {
+  if (!ch) return 0;
+  void* ptrs[] = {ch->lo, ch->hi, ch->y_exp, ch->cov_exp, ch->R, ch->c0, ch->z_mean, ch->z_var, ch->extra,
+                  ch->mean, ch->cov, ch->x_dev, ch->lp_dev, ch->skip, ch->notpd_dev};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  if (ch->stream) cudaStreamDestroy(ch->stream);
+  delete ch;
+  return 0;
+}
+
+extern "C" int64_t gpbt_chain_workspace_bytes(gpbt_chain_t ch) { return ch ? ch->ws_bytes : 0; }
+
+namespace {
+
+// rows of PC-space workspace (z_mean, z_var, extra, skip): grows to the largest N seen
+int ensure_rows(gpbt_chain* ch, int64_t N) {
+  if (N <= ch->cap_rows) return 0;
+  const int64_t cap = std::max<int64_t>(N, 2 * ch->cap_rows);
+  if (ch->z_mean) { cudaFree(ch->z_mean); cudaFree(ch->z_var); cudaFree(ch->extra); cudaFree(ch->skip); }
+  CU(cudaMalloc(&ch->z_mean, (size_t)cap * ch->Q * sizeof(double)));
+  CU(cudaMalloc(&ch->z_var, (size_t)cap * ch->Q * sizeof(double)));
+  CU(cudaMalloc(&ch->extra, (size_t)cap * sizeof(double)));
+  CU(cudaMalloc(&ch->skip, (size_t)cap));
+  ch->ws_bytes += (cap - ch->cap_rows) * (2 * ch->Q * 8 + 9);
+  ch->cap_rows = cap;
+  return 0;
+}
+
+// rows of observable-space workspace for the dense path (mean [rows, M], cov [rows, M, M])
+int64_t dense_chunk_rows(const gpbt_chain* ch, int64_t N) {
+  const size_t per_row = (size_t)ch->M * ch->M * 8 + (size_t)ch->M * 8;
+  size_t free_b = 0, total_b = 0;
+  cudaMemGetInfo(&free_b, &total_b);
+  size_t budget = std::min<size_t>((size_t)24 << 30, free_b / 2 + (size_t)ch->cap_dense * per_row);
+  int64_t rows = (int64_t)std::max<size_t>(budget / per_row, 1);
+  rows = std::min<int64_t>(rows, 32768);
+  return std::min<int64_t>(rows, N);
+}
+
+int ensure_dense(gpbt_chain* ch, int64_t rows) {
+  if (rows <= ch->cap_dense) return 0;
+  if (ch->mean) { cudaFree(ch->mean); cudaFree(ch->cov); }
+  CU(cudaMalloc(&ch->mean, (size_t)rows * ch->M * sizeof(double)));
+  CU(cudaMalloc(&ch->cov, (size_t)rows * ch->M * ch->M * sizeof(double)));
+  ch->ws_bytes += (rows - ch->cap_dense) * ((int64_t)ch->M * ch->M * 8 + (int64_t)ch->M * 8);
+  ch->cap_dense = rows;
+  return 0;
+}
+
+int ensure_io(gpbt_chain* ch, int64_t N) {
+  if (N <= ch->cap_x) return 0;
+  const int64_t cap = std::max<int64_t>(N, 2 * ch->cap_x);
+  if (ch->x_dev) { cudaFree(ch->x_dev); cudaFree(ch->lp_dev); }
+  CU(cudaMalloc(&ch->x_dev, (size_t)cap * ch->p * sizeof(double)));
+  CU(cudaMalloc(&ch->lp_dev, (size_t)cap * sizeof(double)));
+  ch->ws_bytes += (cap - ch->cap_x) * ((int64_t)ch->p * 8 + 8);
+  ch->cap_x = cap;
+  return 0;
+}
+
+// Chain._predict into (mean, cov) for rows [0, N) of X; cov may be null
+int chain_predict_rows(gpbt_chain* ch, const double* X, double extra_scale, double* mean, double* cov,
+                       int64_t N, cudaStream_t st) {
+  if (int r = ensure_rows(ch, N)) return r;
+  const double* extra = nullptr;
+  if (extra_scale != 0.0) {
+    extra_std_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(X, ch->p, N, extra_scale, ch->extra);
+    LAUNCH_CHECK();
+    extra = ch->extra;
+  }
+  for (size_t e = 0; e < ch->emus.size(); e++) {
+    gpbt_emulator_t emu = ch->emus[e];
+    if (int r = run_pc_predict(emu, X, extra, ch->z_mean + ch->q_off[e], ch->z_var + ch->q_off[e], ch->Q, N, st))
+      return r;
+    if (int r = run_backtransform(emu, ch->z_mean + ch->q_off[e], ch->z_var + ch->q_off[e], ch->Q, mean, ch->M,
+                                  cov, ch->M, ch->m_off[e], N, st))
+      return r;
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int gpbt_chain_predict(gpbt_chain_t ch, const double* X, double extra_std_scale, double* mean,
+                                  double* cov, int64_t N, void* stream) {
+  if (!ch || !X || !mean || N < 0) return fail(GPBT_EINVAL, "gpbt_chain_predict: bad argument");
+  const int64_t step = 32768;
+  for (int64_t s = 0; s < N; s += step) {
+    const int64_t nn = std::min(step, N - s);
+    if (int r = chain_predict_rows(ch, X + s * ch->p, extra_std_scale, mean + s * ch->M,
+                                   cov ? cov + (size_t)s * ch->M * ch->M : nullptr, nn, (cudaStream_t)stream))
+      return r;
+  }
+  return 0;
+}
+
+extern "C" int gpbt_log_posterior(gpbt_chain_t ch, const double* X, double oob_value, double* lp, int* n_notpd,
+                                  int64_t N, int path, void* stream) {
+  if (!ch || !X || !lp || N < 0) return fail(GPBT_EINVAL, "gpbt_log_posterior: bad argument");
+  if (N == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (path == GPBT_PATH_AUTO) path = ch->has_lowrank ? GPBT_PATH_LOWRANK : GPBT_PATH_DENSE;
+  if (path == GPBT_PATH_LOWRANK && !ch->has_lowrank)
+    return fail(GPBT_ENOTAPPLICABLE, "low-rank path requested but the chain has no low-rank factors");
+  if (n_notpd) CU(cudaMemsetAsync(n_notpd, 0, sizeof(int), st));
+
+  if (path == GPBT_PATH_LOWRANK) {
+    if (int r = ensure_rows(ch, N)) return r;
+    for (size_t e = 0; e < ch->emus.size(); e++)
+      if (int r = run_pc_predict(ch->emus[e], X, nullptr, ch->z_mean + ch->q_off[e], ch->z_var + ch->q_off[e],
+                                 ch->Q, N, st))
+        return r;
+    LowrankParams prm;
+    prm.X = X; prm.lo = ch->lo; prm.hi = ch->hi; prm.z_mean = ch->z_mean; prm.z_var = ch->z_var;
+    prm.R = ch->R; prm.c0 = ch->c0; prm.lp = lp; prm.n_notpd = n_notpd; prm.s_perp = ch->s_perp;
+    prm.logdetF_half = ch->logdetF_half; prm.oob_value = oob_value; prm.sys_const = kSysConst;
+    prm.N = N; prm.p = ch->p; prm.Q = ch->Q;
+    const size_t smem = lowrank_smem_bytes(ch->Q);
+    if (smem > (size_t)max_optin_smem()) return fail(GPBT_ESHAPE, "low-rank path: Q = %d too large", ch->Q);
+    static size_t configured = 0;
+    if (smem > configured) {
+      CU(cudaFuncSetAttribute(lowrank_loglike_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    lowrank_loglike_kernel<<<(unsigned)((N + kLrWarps - 1) / kLrWarps), kLrWarps * 32, smem, st>>>(prm);
+    LAUNCH_CHECK();
+    return 0;
+  }
+
+  // dense path: (a) -> (b) with the covariance materialised in HBM -> (c), in row chunks
+  const int64_t chunk = dense_chunk_rows(ch, N);
+  if (int r = ensure_dense(ch, chunk)) return r;
+  if (int r = ensure_rows(ch, chunk)) return r;
+  for (int64_t s = 0; s < N; s += chunk) {
+    const int64_t nn = std::min(chunk, N - s);
+    const double* Xs = X + s * ch->p;
+    bounds_mask_kernel<<<(unsigned)((nn + 127) / 128), 128, 0, st>>>(Xs, ch->lo, ch->hi, ch->p, nn, oob_value,
+                                                                     ch->skip, lp + s);
+    LAUNCH_CHECK();
+    if (int r = chain_predict_rows(ch, Xs, 0.0, ch->mean, ch->cov, nn, st)) return r;
+    if (int r = run_chol(ch->mean, ch->y_exp, ch->cov, ch->cov_exp, lp + s, n_notpd, ch->skip, oob_value,
+                         kSysConst, nn, ch->M, st))
+      return r;
+  }
+  return 0;
+}
+
+extern "C" int gpbt_log_posterior_host(gpbt_chain_t ch, const double* X_host, double oob_value, double* lp_host,
+                                       int* n_notpd_host, int64_t N, int path) {
+  if (!ch || !X_host || !lp_host || N < 0) return fail(GPBT_EINVAL, "gpbt_log_posterior_host: bad argument");
+  if (N == 0) return 0;
+  CU(cudaSetDevice(ch->device));
+  if (int r = ensure_io(ch, N)) return r;
+  cudaStream_t st = ch->stream;
+  CU(cudaMemcpyAsync(ch->x_dev, X_host, (size_t)N * ch->p * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (int r = gpbt_log_posterior(ch, ch->x_dev, oob_value, ch->lp_dev, ch->notpd_dev, N, path, st)) return r;
+  CU(cudaMemcpyAsync(lp_host, ch->lp_dev, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (n_notpd_host) CU(cudaMemcpyAsync(n_notpd_host, ch->notpd_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}

@@ -1,0 +1,227 @@
+"""
+Device-side runners: thin Python over the C ABI (include/gpbt.h).  PyTorch is used only as the
+device-memory allocator / stream provider for calls that hand tensors back to the caller.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .state import EmulatorState
+
+_COV_CHUNK_BYTES = 4 << 30  # device bytes of covariance produced per chunk by predict()
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("gpbt_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+    return torch
+
+
+def _stream_ptr(torch):
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def as_rows(X, p=None):
+    """float64 C-contiguous [N, p]; a 1-D input is one row (np.array(X, ndmin=2) in the reference)."""
+    X = np.ascontiguousarray(np.array(X, dtype=np.float64, ndmin=2))
+    if p is not None and X.shape[1] != p:
+        raise ValueError("expected %d parameters per row, got %d" % (p, X.shape[1]))
+    return X
+
+
+class DeviceEmulator:
+    """Emulator.predict on the GPU for one trained emulator (kernels (a) and (b))."""
+
+    def __init__(self, state: EmulatorState):
+        self.state = state
+
+    # -- device tensors in, device tensors out ------------------------------------------------
+    def pc_predict_device(self, X_d, extra_d=None):
+        torch = _torch()
+        st = self.state
+        N = X_d.shape[0]
+        zm = torch.empty((N, st.q), dtype=torch.float64, device=X_d.device)
+        zv = torch.empty_like(zm)
+        _lib.check(_lib.lib.gpbt_pc_predict(
+            st.handle(), X_d.data_ptr(), None if extra_d is None else extra_d.data_ptr(),
+            zm.data_ptr(), zv.data_ptr(), st.q, N, _stream_ptr(torch)))
+        return zm, zv
+
+    def predict_device(self, X_d, return_cov=True, extra_d=None):
+        torch = _torch()
+        st = self.state
+        N = X_d.shape[0]
+        zm, zv = self.pc_predict_device(X_d, extra_d)
+        mean = torch.empty((N, st.m), dtype=torch.float64, device=X_d.device)
+        cov = torch.empty((N, st.m, st.m), dtype=torch.float64, device=X_d.device) if return_cov else None
+        _lib.check(_lib.lib.gpbt_backtransform(
+            st.handle(), zm.data_ptr(), zv.data_ptr(), st.q, mean.data_ptr(), st.m,
+            None if cov is None else cov.data_ptr(), st.m, 0, N, _stream_ptr(torch)))
+        return (mean, cov) if return_cov else mean
+
+    # -- numpy in, numpy out (the reference's signature) --------------------------------------
+    def predict(self, X, return_cov=True, extra_std=0):
+        torch = _torch()
+        st = self.state
+        X = as_rows(X, st.p)
+        N = X.shape[0]
+        extra = np.asarray(extra_std, dtype=np.float64).reshape(-1)
+        if extra.size == 1:
+            extra = None if extra[0] == 0.0 else np.full(N, extra[0])
+        elif extra.size != N:
+            raise ValueError("extra_std must be a scalar or have one entry per row of X")
+        mean = np.empty((N, st.m))
+        cov = np.empty((N, st.m, st.m)) if return_cov else None
+        rows = N if not return_cov else max(1, min(N, _COV_CHUNK_BYTES // (8 * st.m * st.m)))
+        for s in range(0, N, rows):
+            e = min(N, s + rows)
+            X_d = torch.from_numpy(X[s:e]).cuda()
+            extra_d = None if extra is None else torch.from_numpy(np.ascontiguousarray(extra[s:e])).cuda()
+            out = self.predict_device(X_d, return_cov, extra_d)
+            if return_cov:
+                mean[s:e] = out[0].cpu().numpy()
+                cov[s:e] = out[1].cpu().numpy()
+            else:
+                mean[s:e] = out.cpu().numpy()
+        return (mean, cov) if return_cov else mean
+
+
+def mvn_loglike_batch(dY, cov, notpd_value=-np.inf):
+    """Batched mvn_loglike (src/mcmc.py:23-65) for dY [N, m], cov [N, m, m] (NumPy in/out)."""
+    torch = _torch()
+    dY = np.ascontiguousarray(np.array(dY, dtype=np.float64, ndmin=2))
+    cov = np.ascontiguousarray(np.asarray(cov, dtype=np.float64)).reshape(dY.shape[0], dY.shape[1], dY.shape[1])
+    N, m = dY.shape
+    out = np.empty(N)
+    rows = max(1, min(N, _COV_CHUNK_BYTES // (8 * m * m)))
+    for s in range(0, N, rows):
+        e = min(N, s + rows)
+        y_d = torch.from_numpy(dY[s:e]).cuda()
+        c_d = torch.from_numpy(cov[s:e]).cuda()   # device copy; the kernel factorises it in place
+        lp_d = torch.empty(e - s, dtype=torch.float64, device="cuda")
+        _lib.check(_lib.lib.gpbt_mvn_loglike(y_d.data_ptr(), None, c_d.data_ptr(), None, lp_d.data_ptr(),
+                                             None, float(notpd_value), e - s, m, _stream_ptr(torch)))
+        out[s:e] = lp_d.cpu().numpy()
+    return out
+
+
+class DeviceChain:
+    """Everything between X[N, p] and lp[N] for a list of emulators + experimental data
+    (gpbt_chain_t).  Builds the low-rank factors on the host when every emulator is PCA-mode."""
+
+    def __init__(self, states, lo, hi, y_exp, cov_exp, lowrank=True):
+        self.states = list(states)
+        self.p = self.states[0].p
+        self.M = sum(s.m for s in self.states)
+        self.Q = sum(s.q for s in self.states)
+        self.lo = np.ascontiguousarray(lo, dtype=np.float64).reshape(self.p)
+        self.hi = np.ascontiguousarray(hi, dtype=np.float64).reshape(self.p)
+        self.y_exp = np.ascontiguousarray(y_exp, dtype=np.float64).reshape(self.M)
+        self.cov_exp = np.ascontiguousarray(cov_exp, dtype=np.float64).reshape(self.M, self.M)
+        self.lowrank = None
+        if lowrank and all(not (s.no_pca or s.exp_diag) for s in self.states) and self.Q <= self.M:
+            self.lowrank = lowrank_factors(self.states, self.y_exp, self.cov_exp)
+        self._handle = None
+
+    def handle(self):
+        if self._handle is None:
+            h = C.c_void_p()
+            arr = (C.c_void_p * len(self.states))(*[s.handle() for s in self.states])
+            hp = _lib.host_ptr
+            lr = self.lowrank
+            _lib.check(_lib.lib.gpbt_chain_create(
+                C.byref(h), arr, len(self.states), self.p, hp(self.lo), hp(self.hi), hp(self.y_exp),
+                hp(self.cov_exp), hp(lr["R"]) if lr else None, hp(lr["c0"]) if lr else None,
+                lr["s_perp"] if lr else 0.0, lr["logdetF_half"] if lr else 0.0))
+            self._handle = h
+        return self._handle
+
+    def release(self):
+        if self._handle is not None:
+            _lib.lib.gpbt_chain_destroy(self._handle)
+            self._handle = None
+
+    @staticmethod
+    def _path(path):
+        return {None: _lib.PATH_AUTO, "auto": _lib.PATH_AUTO, "dense": _lib.PATH_DENSE,
+                "lowrank": _lib.PATH_LOWRANK}[path]
+
+    def log_target(self, X, oob_value, path=None):
+        """Host buffers in/out through gpbt_log_posterior_host (H2D, kernels, D2H, one sync)."""
+        _torch()
+        X = as_rows(X, self.p)
+        lp = np.empty(X.shape[0])
+        notpd = C.c_int(0)
+        _lib.check(_lib.lib.gpbt_log_posterior_host(
+            self.handle(), _lib.host_ptr(X), float(oob_value), _lib.host_ptr(lp), C.byref(notpd),
+            X.shape[0], self._path(path)))
+        self.last_notpd = notpd.value
+        return lp
+
+    def log_target_device(self, X_d, oob_value, lp_d=None, path=None):
+        """Device tensors in/out on torch's current stream; no synchronisation."""
+        torch = _torch()
+        N = X_d.shape[0]
+        if lp_d is None:
+            lp_d = torch.empty(N, dtype=torch.float64, device=X_d.device)
+        _lib.check(_lib.lib.gpbt_log_posterior(
+            self.handle(), X_d.data_ptr(), float(oob_value), lp_d.data_ptr(), None, N,
+            self._path(path), _stream_ptr(torch)))
+        return lp_d
+
+    def predict(self, X, extra_std=0.0, return_cov=True):
+        """Chain._predict (src/mcmc.py:153-166): mean [N, M], block-diagonal cov [N, M, M]."""
+        torch = _torch()
+        X = as_rows(X, self.p)
+        N = X.shape[0]
+        mean = np.empty((N, self.M))
+        cov = np.empty((N, self.M, self.M)) if return_cov else None
+        rows = N if not return_cov else max(1, min(N, _COV_CHUNK_BYTES // (8 * self.M * self.M)))
+        for s in range(0, N, rows):
+            e = min(N, s + rows)
+            X_d = torch.from_numpy(X[s:e]).cuda()
+            mean_d = torch.empty((e - s, self.M), dtype=torch.float64, device="cuda")
+            cov_d = torch.empty((e - s, self.M, self.M), dtype=torch.float64, device="cuda") if return_cov else None
+            _lib.check(_lib.lib.gpbt_chain_predict(
+                self.handle(), X_d.data_ptr(), float(extra_std), mean_d.data_ptr(),
+                None if cov_d is None else cov_d.data_ptr(), e - s, _stream_ptr(torch)))
+            mean[s:e] = mean_d.cpu().numpy()
+            if return_cov:
+                cov[s:e] = cov_d.cpu().numpy()
+        return (mean, cov) if return_cov else mean
+
+
+def lowrank_factors(states, y_exp, cov_exp):
+    """Host set-up (once per chain) of the exact low-rank form used by lowrank_loglike.cuh:
+        C_w = F + U^T diag(v_w) U,  F = blockdiag(Ctrunc_e) + cov_exp,  U = blockdiag(A_e)
+        L_F^-1 U^T = Qb R,  c0 = Qb^T L_F^-1 (mu - y_exp),  s_perp = |(I - Qb Qb^T) L_F^-1 (mu - y_exp)|^2
+    (reference quantities: src/emulator.py:335-363, src/mcmc.py:153-166, 288-290)."""
+    from scipy.linalg import cholesky, qr, solve_triangular
+    M = sum(s.m for s in states)
+    Q = sum(s.q for s in states)
+    F = np.array(cov_exp, dtype=np.float64)
+    U = np.zeros((Q, M))
+    mu = np.empty(M)
+    qo = mo = 0
+    for s in states:
+        F[mo:mo + s.m, mo:mo + s.m] += s.Ctrunc
+        U[qo:qo + s.q, mo:mo + s.m] = s.A
+        mu[mo:mo + s.m] = s.mu
+        qo += s.q
+        mo += s.m
+    LF = cholesky(F, lower=True, check_finite=True)
+    Bt = solve_triangular(LF, U.T, lower=True)          # [M, Q]
+    Qb, R = qr(Bt, mode="economic")                     # Bt = Qb R
+    sgn = np.sign(np.diag(R))
+    sgn[sgn == 0] = 1.0
+    Qb, R = Qb * sgn, R * sgn[:, None]                  # positive diagonal (cosmetic)
+    w0 = solve_triangular(LF, mu - y_exp, lower=True)
+    c0 = Qb.T @ w0
+    perp = w0 - Qb @ c0
+    perp -= Qb @ (Qb.T @ perp)                          # one re-orthogonalisation step
+    return dict(R=np.ascontiguousarray(np.triu(R)), c0=np.ascontiguousarray(c0),
+                s_perp=float(perp @ perp), logdetF_half=float(np.log(np.diag(LF)).sum()))

@@ -1,0 +1,183 @@
+"""
+Drop-in for the reference's `src/emulator.py` Emulator with `predict` on the B200.
+
+What stays as in the reference (it is offline, one-off work that produces the state the hot path
+consumes): reading the training pickle, StandardScaler -> PCA(whiten) and
+the scikit-learn GaussianProcessRegressor fits (src/emulator.py:257-363, 378-415).
+
+What is replaced: `predict` (src/emulator.py:465-605).  The trained quantities are extracted into
+an `EmulatorState`, uploaded once, and every call runs kernels (a) pc_predict and (b)
+backtransform through the C ABI (include/gpbt.h).  There is no CPU prediction path.
+"""
+from __future__ import annotations
+
+import logging
+import pickle
+
+import numpy as np
+
+from . import parse_model_parameter_file
+from .device import DeviceEmulator
+from .state import GPR_ALPHA, EmulatorState
+
+log = logging.getLogger(__name__)
+
+
+def read_training_pickle(path, log_trafo=False, max_rel_uncertainty=0.1):
+    """Training set in the reference's format (src/emulator.py:378-415):
+    {event_id: {"parameter": [p], "obs": [2, m]}}; row 0 of obs is the value, row 1 its statistical
+    error.  Events are taken in ascending integer id; an event whose largest relative error exceeds
+    `max_rel_uncertainty` is dropped.  With `log_trafo` the observables become log|y| and the errors
+    relative errors.  Returns (design [nev, p], data [nev, m], err [nev, m], n_dropped)."""
+    with open(path, "rb") as fh:
+        events = pickle.load(fh)
+    design, data, err, dropped = [], [], [], 0
+    for key in sorted(events, key=int):
+        val, sig = np.asarray(events[key]["obs"], dtype=np.float64)
+        if np.abs(sig / (val + 1e-16)).max() > max_rel_uncertainty:
+            dropped += 1
+            continue
+        design.append(np.asarray(events[key]["parameter"], dtype=np.float64))
+        if log_trafo:
+            data.append(np.log(np.abs(val) + 1e-30))
+            err.append(np.abs(sig / (val + 1e-30)))
+        else:
+            data.append(val)
+            err.append(sig)
+    return (np.array(design), np.array(data), np.nan_to_num(np.abs(np.array(err))), dropped)
+
+
+class Emulator:
+    """PCA + independent-GP emulator; same constructor and public methods as the reference class.
+
+    Attributes kept for callers / notebooks: design_min, design_max, npc, nev, nobs, model_data,
+    model_data_err, design_points, scaler, pca, gps, _trans_matrix, _var_trans, _cov_trunc."""
+
+    def __init__(self, training_set_path=".", parameter_file="ABCD.txt", npc=10, nrestarts=0,
+                 logTrafo=False, parameterTrafoPCA=False, max_rel_uncertainty_data=0.1,
+                 exp_and_cov_diagonal=False, perform_no_PCA=False):
+        from sklearn.decomposition import PCA
+        from sklearn.preprocessing import StandardScaler
+        if exp_and_cov_diagonal and not logTrafo:
+            raise ValueError("exp_and_cov_diagonal can only be set to True if logTrafo is True.")
+        if parameterTrafoPCA:
+            raise NotImplementedError(
+                "parameterTrafoPCA (src/emulator.py:79-99, 492-551) is a host pre-transform that "
+                "needs >= 19 parameters; it is outside this accelerated path (DESIGN.md, scope)")
+        self.logTrafo_ = logTrafo
+        self.parameterTrafoPCA_ = False
+        self.max_rel_uncertainty_data_ = max_rel_uncertainty_data
+        self.exp_and_cov_diagonal_ = exp_and_cov_diagonal
+        self.perform_no_PCA_ = perform_no_PCA
+        self.npc = npc
+        self.nrestarts = nrestarts
+
+        self.design_points, self.model_data, self.model_data_err, dropped = read_training_pickle(
+            training_set_path, logTrafo, max_rel_uncertainty_data)
+        self.design_points_org_ = self.design_points.copy()
+        log.info("Training dataset size: %d, discarded points: %d", len(self.model_data), dropped)
+        self.nev, self.nobs = self.model_data.shape
+
+        self.pardict = parse_model_parameter_file(parameter_file)
+        bounds = np.array([[v[1], v[2]] for v in self.pardict.values()], dtype=np.float64)
+        self.design_min, self.design_max = bounds[:, 0].copy(), bounds[:, 1].copy()
+
+        self.scaler = StandardScaler(copy=False)
+        self.pca = PCA(copy=False, whiten=True, svd_solver="full")
+        self.gps = []
+        self._state = None
+        self._device = None
+
+    # ---- training (offline, scikit-learn, as the reference) -----------------------------------
+    def trainEmulatorAutoMask(self):
+        self.trainEmulator([True] * self.nev)
+
+    def _make_kernel(self, kernel_type):
+        from sklearn.gaussian_process import kernels
+        span = self.design_max - self.design_min
+        if kernel_type == "RBF":
+            base = kernels.RBF(length_scale=span, length_scale_bounds=np.outer(span, (1e-1, 1e2)))
+        elif kernel_type == "Matern":
+            base = kernels.Matern(length_scale=span, length_scale_bounds=np.outer(span, (1e-3, 1e5)), nu=1.5)
+        else:
+            raise ValueError("Unknown kernel type: {}".format(kernel_type))
+        noise = kernels.WhiteKernel(noise_level=.05, noise_level_bounds=(1e-2, 1e2))
+        return 1. * base + noise
+
+    def trainEmulator(self, eventMask, kernel_type="RBF"):
+        from sklearn.gaussian_process import GaussianProcessRegressor
+        mask = np.asarray(eventMask, dtype=bool)
+        Y = self.scaler.fit_transform(self.model_data[mask, :])
+        if self.perform_no_PCA_:
+            Z = Y
+        else:
+            Z = self.pca.fit_transform(Y)[:, :self.npc]
+            log.info("%d PCs explain %.5f of variance", self.npc,
+                     self.pca.explained_variance_ratio_[:self.npc].sum())
+        theta = self.design_points[mask, :]
+        kernel = self._make_kernel(kernel_type)
+        self.gps = [GaussianProcessRegressor(kernel=kernel, alpha=GPR_ALPHA,
+                                             n_restarts_optimizer=self.nrestarts,
+                                             copy_X_train=False).fit(theta, z) for z in Z.T]
+        self._kernel_type = kernel_type
+        self._finish_training()
+
+    def _finish_training(self):
+        """Transform matrices of the PCA mode (src/emulator.py:330-363)."""
+        if not self.perform_no_PCA_:
+            self._trans_matrix = (self.pca.components_
+                                  * np.sqrt(self.pca.explained_variance_[:, np.newaxis])
+                                  * self.scaler.scale_)
+            kept, dropped = self._trans_matrix[:self.npc], self._trans_matrix[self.npc:]
+            self._cov_trunc = dropped.T @ dropped
+            self._cov_trunc.flat[::self.nobs + 1] += 1e-4 * self.scaler.var_
+        self._state = None
+        self._device = None
+
+    @property
+    def _var_trans(self):
+        # the reference precomputes this [npc, nobs^2] array (src/emulator.py:353-355); kernel (b)
+        # never needs it, so it is only materialised if a caller asks
+        kept = self._trans_matrix[:self.npc]
+        return np.einsum("ki,kj->kij", kept, kept).reshape(self.npc, self.nobs ** 2)
+
+    # ---- state / device --------------------------------------------------------------------
+    @property
+    def state(self) -> EmulatorState:
+        if self._state is None:
+            if not self.gps:
+                raise RuntimeError("emulator is not trained")
+            self._state = EmulatorState.from_trained(self, keep_L=True)
+        return self._state
+
+    @classmethod
+    def from_state(cls, state: EmulatorState, design_min=None, design_max=None):
+        """An Emulator that only predicts (no training data), around an existing state."""
+        self = cls.__new__(cls)
+        self.logTrafo_ = state.exp_diag
+        self.parameterTrafoPCA_ = False
+        self.exp_and_cov_diagonal_ = state.exp_diag
+        self.perform_no_PCA_ = state.no_pca
+        self.npc, self.nobs, self.nev = state.q, state.m, state.n
+        self.design_min, self.design_max = design_min, design_max
+        self.gps = []
+        self._state, self._device = state, None
+        return self
+
+    def _dev(self) -> DeviceEmulator:
+        if self._device is None:
+            self._device = DeviceEmulator(self.state)
+        return self._device
+
+    # ---- the hot path ------------------------------------------------------------------------
+    def predict(self, X, return_cov=True, extra_std=0):
+        """Model output at X [nsamples, ndim]: mean [nsamples, nobs] and, with `return_cov`, the
+        observable-space covariance [nsamples, nobs, nobs] per sample.  `extra_std` (scalar or one
+        value per sample) is added in quadrature to every GP's predictive standard deviation."""
+        return self._dev().predict(X, return_cov=return_cov, extra_std=extra_std)
+
+    # ---- pickling: device handles never travel -------------------------------------------------
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d["_device"] = None
+        return d

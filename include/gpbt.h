@@ -1,0 +1,139 @@
+/*
+ * gpbt.h -- C ABI of libgpbt_b200.so: the B200 (sm_100a) implementation of GPBayesTools-HIC's
+ * batched "PCA-GP emulator -> Gaussian log-likelihood" hot path.
+ *
+ * The reference is pure Python and has no FFI; the operator interfaces this ABI sits behind are
+ * the Python call signatures (paths are under /root/reference):
+ *
+ *   Emulator.predict(X, return_cov, extra_std)     src/emulator.py:465-605
+ *   Chain._predict(X, extra_std)                   src/mcmc.py:153-166
+ *   mvn_loglike(y, cov)                            src/mcmc.py:23-65
+ *   Chain.log_likelihood(X, ..., finite)           src/mcmc.py:188-222
+ *   Chain.log_posterior(X, ...)                    src/mcmc.py:261-299
+ *
+ * Conventions
+ *   - all floating point data is IEEE binary64, row-major, contiguous unless a leading dimension
+ *     is given;  N = walkers (rows of X), p = parameters, n = design points, q = emulated PCs,
+ *     m = observables of one emulator, M = observables of the whole chain, Q = PCs of the chain.
+ *   - "_dev" arguments are device pointers on the CUDA device that was current when the handle
+ *     was created; "_host" arguments are host pointers.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Device entry
+ *     points only enqueue work; they never synchronise.
+ *   - every function returns 0 on success, a positive cudaError_t value on a CUDA failure, or a
+ *     negative GPBT_E* code.  gpbt_last_error() returns a thread-local message.
+ *   - there is no CPU implementation behind any entry point.
+ */
+#ifndef GPBT_H
+#define GPBT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gpbt_emulator* gpbt_emulator_t; /* device-resident trained state of one emulator */
+typedef struct gpbt_chain* gpbt_chain_t;       /* emulators + experimental data + workspaces    */
+
+enum { GPBT_KERNEL_RBF = 0, GPBT_KERNEL_MATERN32 = 1 };
+enum { GPBT_FLAG_NO_PCA = 1, GPBT_FLAG_EXP_DIAG = 2 };
+enum { GPBT_PATH_AUTO = 0, GPBT_PATH_DENSE = 1, GPBT_PATH_LOWRANK = 2 };
+enum {
+  GPBT_EINVAL = -1,   /* bad argument                                              */
+  GPBT_ESHAPE = -2,   /* shape outside what the kernels support (message says why) */
+  GPBT_ENOTAPPLICABLE = -3 /* requested path cannot represent this chain           */
+};
+
+const char* gpbt_last_error(void);
+int gpbt_version(void);
+
+/* ---- emulator state --------------------------------------------------------------------- *
+ * Replaces the sklearn objects a trained reference Emulator carries (src/emulator.py:309-363):
+ *   Xtr   [n,p]    gp.X_train_ (shared by all GPs, copy_X_train=False, :312)
+ *   ell   [q,p]    gp.kernel_.k1.k2.length_scale      c [q]  gp.kernel_.k1.k1.constant_value
+ *   sn    [q]      gp.kernel_.k2.noise_level          alpha [q,n]  gp.alpha_
+ *   Linv  [q,n,n]  inverse of gp.L_ (lower triangular; the caller inverts L_ once in FP64)
+ *   A     [q,m]    _trans_matrix[:npc]  (PCA mode; ignored with GPBT_FLAG_NO_PCA)
+ *   mu    [m]      scaler.mean_         scale [m]  scaler.scale_ (used with GPBT_FLAG_NO_PCA)
+ *   Ctrunc[m,m]    _cov_trunc           (PCA mode; NULL with GPBT_FLAG_NO_PCA)
+ * All pointers are HOST pointers; the data is copied to the current device.                 */
+int gpbt_emulator_create(gpbt_emulator_t* out, int p, int n, int q, int m, int kernel_kind,
+                         int flags, const double* Xtr_host, const double* ell_host,
+                         const double* c_host, const double* sn_host, const double* alpha_host,
+                         const double* Linv_host, const double* A_host, const double* mu_host,
+                         const double* scale_host, const double* Ctrunc_host);
+int gpbt_emulator_destroy(gpbt_emulator_t emu);
+
+/* ---- kernel (a): per-(walker, PC) cross-kernel + GP mean + predictive variance ----------- *
+ * Replaces [gp.predict(X, return_cov=True) for gp in self.gps] + diagonal extraction + the
+ * extra_std**2 term (src/emulator.py:553, 573-579; sklearn _gpr.py:446-466).
+ *   z_mean[i*ldz + j], z_var[i*ldz + j]  for walker i, PC j;   extra_std_dev may be NULL.     */
+int gpbt_pc_predict(gpbt_emulator_t emu, const double* X_dev, const double* extra_std_dev,
+                    double* z_mean_dev, double* z_var_dev, int64_t ldz, int64_t N, void* stream);
+
+/* ---- kernel (b): PCA back-transform to observable space ---------------------------------- *
+ * Replaces _inverse_transform / scaler.inverse_transform, exp(), np.dot(gp_var,_var_trans) +
+ * _cov_trunc and the exp_and_cov_diagonal rewrite (src/emulator.py:558-601).
+ *   mean_dev[i*ld_mean + col_off + o]                         (always written)
+ *   cov_dev [i*ld_cov*ld_cov + (col_off+o)*ld_cov + col_off + o']   (skipped when NULL)
+ * With ld_cov > m the rows col_off..col_off+m-1 of each walker's matrix are written across ALL
+ * ld_cov columns (zeros outside the diagonal block), which is how Chain._predict's block-diagonal
+ * covariance (src/mcmc.py:153-166) is assembled without a separate memset.                   */
+int gpbt_backtransform(gpbt_emulator_t emu, const double* z_mean_dev, const double* z_var_dev,
+                       int64_t ldz, double* mean_dev, int64_t ld_mean, double* cov_dev,
+                       int64_t ld_cov, int64_t col_off, int64_t N, void* stream);
+
+/* ---- kernel (c): batched Cholesky log-likelihood ------------------------------------------ *
+ * Replaces list(map(mvn_loglike, dY, cov)) (src/mcmc.py:23-65, 293) including dY = mean - y_exp
+ * and cov + expdata_cov (src/mcmc.py:288-290):
+ *   lp[i] = -1/2 y_i^T C_i^-1 y_i - sum(log(diag(chol(C_i)))),   y_i = mean_i - y_exp (y_exp may
+ *   be NULL), C_i = cov_i + cov_add (cov_add may be NULL).
+ * cov_dev [N,m,m] is OVERWRITTEN (its lower triangle receives the Cholesky factor, as dpotrf
+ * does to its own copy).  Walkers whose matrix is not positive definite get lp = notpd_value and
+ * increment *n_notpd_dev (may be NULL); the reference's own check is broken (both branches test
+ * info < 0, src/mcmc.py:44-54) and would return garbage there.                               */
+int gpbt_mvn_loglike(const double* mean_dev, const double* y_exp_dev, double* cov_dev,
+                     const double* cov_add_dev, double* lp_dev, int* n_notpd_dev,
+                     double notpd_value, int64_t N, int m, void* stream);
+
+/* ---- chain: everything between X[N,p] and lp[N] ------------------------------------------ *
+ * lo/hi [p]: Chain.min/max; y_exp [M]: Chain.expdata; cov_exp [M,M]: Chain.expdata_cov
+ * (src/mcmc.py:104-142).  The optional low-rank factors describe the exact identity
+ *     C_w = F + U^T diag(v_w) U,  F = blockdiag(Ctrunc_e) + cov_exp  (walker independent)
+ * through  L_F^-1 U^T = Qb R :  R [Q,Q] upper triangular, c0 = Qb^T L_F^-1 (mu - y_exp) [Q],
+ * s_perp = |(I - Qb Qb^T) L_F^-1 (mu - y_exp)|^2, logdetF_half = sum(log(diag(L_F))).
+ * Pass R_host = NULL when the chain has a no-PCA / exp-diag emulator (dense path only).
+ * All pointers are HOST pointers.                                                             */
+int gpbt_chain_create(gpbt_chain_t* out, const gpbt_emulator_t* emus, int n_emu, int p,
+                      const double* lo_host, const double* hi_host, const double* y_exp_host,
+                      const double* cov_exp_host, const double* R_host, const double* c0_host,
+                      double s_perp, double logdetF_half);
+int gpbt_chain_destroy(gpbt_chain_t chain);
+
+/* Chain._predict on device buffers: mean [N,M], cov [N,M,M] (cov may be NULL).               */
+int gpbt_chain_predict(gpbt_chain_t chain, const double* X_dev, double extra_std_scale,
+                       double* mean_dev, double* cov_dev, int64_t N, void* stream);
+
+/* Chain.log_posterior / log_likelihood: bounds mask (strict, src/mcmc.py:275-276), emulators,
+ * likelihood and the constant 2*log(1e-16) (src/mcmc.py:296-297).  Rows outside the box get
+ * oob_value (-inf, or -1e300 for finite=True).  path: GPBT_PATH_AUTO picks LOWRANK when the
+ * chain was created with R, else DENSE ((a) -> (b) -> (c) with the covariance in HBM).
+ * n_notpd_dev (may be NULL) counts non-positive-definite walkers.                            */
+int gpbt_log_posterior(gpbt_chain_t chain, const double* X_dev, double oob_value, double* lp_dev,
+                       int* n_notpd_dev, int64_t N, int path, void* stream);
+
+/* Same with HOST buffers: pinned staging, H2D of X, kernels, D2H of lp, one synchronisation.
+ * This is the call behind Chain.log_posterior(X: np.ndarray) -> np.ndarray.                  */
+int gpbt_log_posterior_host(gpbt_chain_t chain, const double* X_host, double oob_value,
+                            double* lp_host, int* n_notpd_host, int64_t N, int path);
+
+/* bytes of device workspace the chain currently holds (grows with the largest N seen)        */
+int64_t gpbt_chain_workspace_bytes(gpbt_chain_t chain);
+
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches)      */
+int64_t gpbt_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPBT_H */

@@ -161,12 +161,11 @@ def make_case(name, syn, Emulator, Chain, mvn_loglike, p, n, emus, N, seed, keep
     # mvn_loglike pin on the first rows' (dY, cov)
     dY = pm - ch.expdata
     cv = pc + ch.expdata_cov
-    out["mvn_y"] = dY
-    out["mvn_cov"] = cv
+    # (mvn inputs are chain_mean - y_exp and chain_cov + cov_exp; not stored twice)
     out["mvn_val"] = np.array([mvn_loglike(a, b) for a, b in zip(dY, cv)])
     # full-covariance variant (BASELINE config 4): add a PSD systematic term to expdata_cov
     ch.expdata_cov = ch.expdata_cov + syn.systematic_cov(m_total)
-    out["cov_exp_sys"] = np.array(ch.expdata_cov)
+    # (cov_exp_sys = cov_exp + synthetic.systematic_cov(m_total); deterministic, not stored)
     out["lp_posterior_sys"] = ch.log_posterior(X)
 
     path = os.path.join(HERE, name + ".npz")
@@ -184,7 +183,7 @@ CASES = {
     "c1_multi": (5, 100, [dict(m=30, q=8, kind="RBF"), dict(m=20, q=6, kind="Matern")], 64, 7, 8),
     "odd_shape": (3, 37, [dict(m=13, q=5, kind="RBF")], 33, 8, 8),
 }
-C2_CASE = {"c2_rbf": (17, 500, [dict(m=300, q=20, kind="RBF")], 1024, 3, 2)}
+C2_CASE = {"c2_rbf": (17, 500, [dict(m=300, q=20, kind="RBF")], 1024, 3, 1)}
 
 
 def main():

@@ -61,3 +61,18 @@ def oracle_states(g):
             st["Ctrunc"] = g[pre + "Ctrunc"]
         states.append(st)
     return states
+
+
+def synthetic_module():
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location(
+        "gpbt_synthetic", os.path.join(root, "gpbayestools-hic_b200", "synthetic.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def cov_exp_sys(g):
+    """expdata_cov + the PSD systematic term make_golden.py added for lp_posterior_sys."""
+    return g["cov_exp"] + synthetic_module().systematic_cov(g["cov_exp"].shape[0])

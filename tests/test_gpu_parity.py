@@ -1,0 +1,165 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against (1) golden vectors produced by the
+unmodified reference and (2) the oracle on the same inputs.  Run with -m gpu on the B200 box."""
+import numpy as np
+import pytest
+
+from oracle import gp_oracle as orc
+from tests import goldens
+from tests.helpers import ABS_LP, REL, pc_scale, product_states, rel_err, scaled_err
+
+pytestmark = pytest.mark.gpu
+CASES = [c for c in goldens.SMALL_CASES + ["c2_rbf"] if c in goldens.available()]
+
+
+@pytest.fixture(scope="module", params=CASES)
+def case(request):
+    g = goldens.load(request.param)
+    states, sts = product_states(g)
+    return request.param, g, states, sts
+
+
+def test_pc_predict(case):
+    """kernel (a): PC-space mean / variance vs sklearn's own per-GP predict (golden)."""
+    import torch
+    from gpbt_b200.device import DeviceEmulator
+    name, g, states, sts = case
+    Xin = np.ascontiguousarray(g["X"][g["inside"]])
+    for e, (st, ost) in enumerate(zip(states, sts)):
+        zm, zv = DeviceEmulator(st).pc_predict_device(torch.from_numpy(Xin).cuda())
+        zm, zv = zm.cpu().numpy(), zv.cpu().numpy()
+        # variance: 1e-9 relative (it already contains the k** - |L^-1 k|^2 cancellation)
+        assert rel_err(zv, g["e%d_z_var" % e]) <= REL, name
+        # mean: an ill-conditioned sum -> error measured against sum |k_i alpha_i|
+        scale = pc_scale(ost, Xin)
+        assert np.max(np.abs(zm - g["e%d_z_mean" % e]) / scale) <= 1e-13, name
+        om, ov = orc.pc_predict(ost, Xin)
+        assert rel_err(zv, ov) <= REL
+        assert np.max(np.abs(zm - om) / scale) <= 1e-13
+
+
+def test_emulator_predict(case):
+    """boundary #1: Emulator.predict(X, return_cov=True, extra_std=arr) (kernels (a)+(b))."""
+    from gpbt_b200.emulator import Emulator
+    name, g, states, sts = case
+    Xin = g["X"][g["inside"]]
+    for e, st in enumerate(states):
+        emu = Emulator.from_state(st)
+        rows = g["e%d_mean_x" % e].shape[0]
+        mean, cov = emu.predict(Xin[:rows], return_cov=True, extra_std=g["extra_std"][:rows])
+        assert rel_err(mean, g["e%d_mean_x" % e]) <= REL, name
+        ref = g["e%d_cov_x" % e]
+        assert scaled_err(cov, ref) <= REL, name
+        d = np.arange(ref.shape[1])
+        assert rel_err(cov[:, d, d], ref[:, d, d]) <= REL, name
+        assert np.array_equal(cov, np.swapaxes(cov, 1, 2)) or scaled_err(cov, np.swapaxes(cov, 1, 2)) < 1e-15
+        mean0 = emu.predict(Xin[:256], return_cov=False)
+        assert rel_err(mean0, g["e%d_mean0" % e]) <= REL, name
+        # scalar extra_std (the reference's default 0 breaks on NumPy 2; ours must not)
+        m1 = emu.predict(Xin[:4], return_cov=False, extra_std=0)
+        assert np.array_equal(m1, mean0[:4])
+
+
+def test_chain_predict_and_mvn(case):
+    """Chain._predict layout (block-diagonal) and kernel (c) vs the reference's mvn_loglike."""
+    from gpbt_b200.device import DeviceChain, mvn_loglike_batch
+    from gpbt_b200.mcmc import mvn_loglike
+    name, g, states, sts = case
+    ch = DeviceChain(states, g["lo"], g["hi"], g["y_exp"].reshape(-1), g["cov_exp"])
+    Xin = g["X"][g["inside"]]
+    rows = g["chain_mean"].shape[0]
+    mean, cov = ch.predict(Xin[:rows], 0.0)
+    assert rel_err(mean, g["chain_mean"]) <= REL, name
+    assert scaled_err(cov, g["chain_cov"]) <= REL, name
+    assert np.array_equal(cov == 0.0, g["chain_cov"] == 0.0) or len(states) == 1
+    dY = g["chain_mean"] - g["y_exp"]
+    C = g["chain_cov"] + g["cov_exp"]
+    vals = mvn_loglike_batch(dY, C)
+    assert np.max(np.abs(vals - g["mvn_val"])) <= ABS_LP, name
+    assert abs(mvn_loglike(dY[0], C[0]) - g["mvn_val"][0]) <= ABS_LP
+    bad = C[0].copy()
+    bad[3, 3] = -1.0
+    with pytest.raises(np.linalg.LinAlgError):
+        mvn_loglike(dY[0], bad)
+    ch.release()
+
+
+@pytest.mark.parametrize("path", ["lowrank", "dense"])
+def test_log_posterior(case, path):
+    """boundary #2: Chain.log_posterior / log_likelihood values and out-of-bounds conventions."""
+    from gpbt_b200.device import DeviceChain
+    name, g, states, sts = case
+    ch = DeviceChain(states, g["lo"], g["hi"], g["y_exp"].reshape(-1), g["cov_exp"])
+    if path == "lowrank" and ch.lowrank is None:
+        from gpbt_b200._lib import GpbtError
+        with pytest.raises(GpbtError):
+            ch.log_target(g["X"], -np.inf, path="lowrank")
+        return
+    ref = g["lp_posterior"]
+    fin = np.isfinite(ref)
+    lp = ch.log_target(g["X"], -np.inf, path=path)
+    assert np.array_equal(np.isneginf(lp), np.isneginf(ref)), name
+    assert np.max(np.abs(lp[fin] - ref[fin])) <= ABS_LP, (name, path)
+    lf = ch.log_target(g["X"], -1e300, path=path)
+    assert np.array_equal(lf == -1e300, g["lp_like_finite"] == -1e300)
+    assert np.max(np.abs(lf[fin] - g["lp_like_finite"][fin])) <= ABS_LP
+    assert ch.last_notpd == 0
+    # N = 1 and 1-D input (PTLMC's probe calls) equal the corresponding batch rows
+    i = int(np.flatnonzero(fin)[0])
+    assert abs(ch.log_target(g["X"][i], -np.inf, path=path)[0] - lp[i]) <= 1e-10
+    ch.release()
+    # full (non-diagonal) experimental covariance, BASELINE config 4
+    ch2 = DeviceChain(states, g["lo"], g["hi"], g["y_exp"].reshape(-1), goldens.cov_exp_sys(g))
+    ls = ch2.log_target(g["X"], -np.inf, path=path)
+    assert np.max(np.abs(ls[fin] - g["lp_posterior_sys"][fin])) <= ABS_LP, (name, path)
+    ch2.release()
+
+
+def test_chain_class_drop_in(tmp_path):
+    """The reference-facing classes end to end: train with this package's Emulator on the
+    reference's file formats, dill round trip, Chain.loadEmulator, log_posterior vs the oracle."""
+    import dill
+    from gpbt_b200 import synthetic
+    from gpbt_b200.emulator import Emulator
+    from gpbt_b200.mcmc import Chain
+    paths = synthetic.write_fixture(str(tmp_path), p=4, n=60, m=20)
+    emu = Emulator(training_set_path=paths["train"], parameter_file=paths["par"], npc=6)
+    emu.trainEmulatorAutoMask()
+    ep = str(tmp_path / "emu.pkl")
+    with open(ep, "wb") as fh:
+        dill.dump(emu, fh)
+    (tmp_path / "mcmc").mkdir()
+    ch = Chain(mcmc_path=str(tmp_path / "mcmc" / "chain.pkl"), expdata_path=paths["exp"],
+               model_parafile=paths["par"])
+    ch.loadEmulator([ep])
+    X = synthetic.walkers(4, 200, seed=12)
+    lp = ch.log_posterior(X)
+    ost = [e.state.oracle_dict() for e in ch.emuList]
+    want = orc.log_posterior(ost, X, ch.min, ch.max, ch.expdata, ch.expdata_cov)
+    fin = np.isfinite(want)
+    assert np.array_equal(np.isneginf(lp), np.isneginf(want))
+    assert np.max(np.abs(lp[fin] - want[fin])) <= ABS_LP
+    assert np.array_equal(ch.log_likelihood(X, finite=True)[~fin], np.full((~fin).sum(), -1e300))
+    assert ch.map(ch.log_posterior, X[:5]).shape == (5,)
+    mean, cov = ch._predict(X[fin][:3])
+    omean, ocov = orc.chain_predict(ost, X[fin][:3], 0.0)
+    assert rel_err(mean, omean) <= REL and scaled_err(cov, ocov) <= REL
+    assert np.max(np.abs(ch.log_likelihood_point_by_point(X[:7]) - lp[:7])[fin[:7]]) <= 1e-10
+
+
+def test_invariances():
+    """Size-independent properties: permutation equivariance over walkers, chunking invariance,
+    tile-width invariance (N small -> narrow tiles, N large -> wide tiles give the same numbers)."""
+    from gpbt_b200.device import DeviceChain
+    g = goldens.load("c1_rbf")
+    states, _ = product_states(g)
+    ch = DeviceChain(states, g["lo"], g["hi"], g["y_exp"].reshape(-1), g["cov_exp"])
+    rng = np.random.default_rng(0)
+    X = rng.uniform(g["lo"], g["hi"], (3000, len(g["lo"])))
+    lp = ch.log_target(X, -np.inf)
+    perm = rng.permutation(len(X))
+    assert np.max(np.abs(ch.log_target(X[perm], -np.inf) - lp[perm])) <= 1e-10
+    parts = np.concatenate([ch.log_target(X[s:s + 37], -np.inf) for s in range(0, 600, 37)])
+    assert np.max(np.abs(parts - lp[:len(parts)])) <= 1e-10
+    dense = ch.log_target(X[:500], -np.inf, path="dense")
+    assert np.max(np.abs(dense - lp[:500])) <= ABS_LP
+    assert ch.log_target(np.empty((0, len(g["lo"]))), -np.inf).shape == (0,)

@@ -56,7 +56,8 @@ def test_chain_and_loglike(case):
     mean, cov = orc.chain_predict(states, Xin[:rows], 0.0)
     assert rel_err(mean, g["chain_mean"]) <= REL
     assert np.max(np.abs(cov - g["chain_cov"])) <= REL * np.max(np.abs(g["chain_cov"]))
-    vals = np.array([orc.mvn_loglike(y, c) for y, c in zip(g["mvn_y"], g["mvn_cov"])])
+    mvn_y, mvn_cov = g["chain_mean"] - g["y_exp"], g["chain_cov"] + g["cov_exp"]
+    vals = np.array([orc.mvn_loglike(y, c) for y, c in zip(mvn_y, mvn_cov)])
     assert np.max(np.abs(vals - g["mvn_val"])) <= ABS_LP
     args = (states, g["X"], g["lo"], g["hi"], g["y_exp"], g["cov_exp"])
     lp = orc.log_posterior(*args)
@@ -67,5 +68,5 @@ def test_chain_and_loglike(case):
     lf = orc.log_likelihood(*args, finite=True)
     assert np.array_equal(lf == -1e300, g["lp_like_finite"] == -1e300)
     assert np.max(np.abs(lf[fin] - g["lp_like_finite"][fin])) <= ABS_LP
-    ls = orc.log_posterior(states, g["X"], g["lo"], g["hi"], g["y_exp"], g["cov_exp_sys"])
+    ls = orc.log_posterior(states, g["X"], g["lo"], g["hi"], g["y_exp"], goldens.cov_exp_sys(g))
     assert np.max(np.abs(ls[fin] - g["lp_posterior_sys"][fin])) <= ABS_LP
