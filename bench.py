@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""
+bench.py -- log-posterior evaluations / second for BASELINE.json's config 2
+(17 parameters, 500 design points, 300 observables, 20 PCs; 4096 particles per GPU per step).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path (Chain.log_posterior) over one fresh batch of walkers.
+  value     device-timed (CUDA events on the launching stream), inputs resident in HBM,
+            L2 flushed between timed steps (outside the events)
+  e2e       the same metric through the host API with HOST buffers (pinned): H2D of X, kernels,
+            (all-gather), D2H of lp, one synchronisation per step -- wall clock
+  roofline  kernel (a) pc_predict alone: algorithmic FP64 flops / CUDA-event time vs. the cuBLAS
+            DGEMM rate measured in this run (MEASURED_PEAKS.json has no FP64 entry)
+  cpu_baseline  the oracle port (NumPy/SciPy restatement of the reference) on a bounded sample,
+            on the host's cores, rank 0, N=1 only
+--impl reference times the CPU restatement of the reference on the host cores (the reference itself
+is pure Python that cannot travel to the GPU box).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "log-posterior evals/sec (walkers x steps)"
+UNIT = "evals/s"
+WORKLOAD = "C2: 17-param JETSCAPE-like design, 500 pts, 300 observables, 20 PCs; pocoMC 4096 particles"
+SHAPE = dict(p=17, n=500, m=300, q=20)
+
+
+def flops_pc_predict(p, n, q):
+    """q n (3p+4) + 2 q n + q n^2 FP64 flops per evaluation (FMA = 2)"""
+    return q * n * (3 * p + 4) + 2 * q * n + q * n * n
+
+
+def load_c2():
+    """Config-2 emulator state: hyper-parameters / alpha / PCA matrices trained by the unmodified
+    reference (tests/golden/c2_rbf.npz); L_ is rebuilt from them as sklearn's fit does."""
+    from tests import goldens
+    g = goldens.load("c2_rbf")
+    return g, goldens.oracle_states(g)
+
+
+def walkers(g, N, seed):
+    """uniform in the box, 1 % of rows pushed out of bounds"""
+    rng = np.random.default_rng(seed)
+    lo, hi = g["lo"], g["hi"]
+    X = rng.uniform(lo, hi, (N, len(lo)))
+    rows = rng.choice(N, max(1, N // 100), replace=False)
+    X[rows, rng.integers(0, len(lo), len(rows))] = hi.max() + 1.0
+    return X
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs"""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows if len(r) >= 6)]
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_port_rate(g, sts, rows, chunk=128, repeats=1, seed=99):
+    """evals/s of the oracle port on `rows` walkers of the same workload (all BLAS threads)."""
+    from oracle import gp_oracle as orc
+    X = walkers(g, rows, seed)
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        orc.log_posterior_chunked(sts, X, g["lo"], g["hi"], g["y_exp"], g["cov_exp"], chunk=chunk)
+        best = min(best, time.perf_counter() - t0)
+    return rows / best, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    g, sts = load_c2()
+    rows = args.cpu_rows
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_port_rate(g, sts, min(rows, 128))
+    times = []
+    for s in range(args.steps):
+        rate, dt = cpu_port_rate(g, sts, rows, seed=100 + s)
+        times.append(dt)
+    total = sum(times)
+    value = rows * args.steps / total
+    cores = os.cpu_count()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rows_per_step": rows,
+                   "note": "CPU restatement of the reference (oracle port, O(N) per row) in chunks of 128 rows"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d walkers per step, chunks of 128 rows, NumPy/SciPy with %d BLAS threads" % (rows, cores)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import gpbt_b200  # noqa: F401
+    from gpbt_b200 import _lib
+    from gpbt_b200.device import DeviceChain, DeviceEmulator
+    from gpbt_b200.dist import ShardedEvaluator
+    from gpbt_b200.state import EmulatorState
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    g, sts = load_c2()
+    states = [EmulatorState.from_arrays(s["kind"], s["Xtr"], s["ell"], s["c"], s["sn"], s["alpha"], s["mu"],
+                                        s["scale"], s.get("A"), s.get("Ctrunc"), L=s["L"], keep_L=False) for s in sts]
+    chain = DeviceChain(states, g["lo"], g["hi"], g["y_exp"].reshape(-1), g["cov_exp"])
+    N, p = args.walkers, len(g["lo"])
+    K, W = args.steps, args.warmup
+    nb = K + W
+    # fresh walkers every step; each rank has its own rows (weak scaling)
+    Xh = [torch.from_numpy(walkers(g, N, 1000 * rank + i)).pin_memory() for i in range(nb)]
+    Xd = [x.to(dev) for x in Xh]
+    ev = ShardedEvaluator(lambda X: chain.log_target_device(X, -np.inf, path=args.path), dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxr(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident leg -------------------------------------------------------------
+    for i in range(W):
+        ev.evaluate_local(Xd[i])
+    barrier()
+    launches0 = _lib.lib.gpbt_launch_count()
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    with ClockSampler(local) as clk:
+        t_wall0 = time.perf_counter()
+        for i in range(K):
+            flush.fill_(i & 0xff)
+            ev0[i].record()
+            out = ev.evaluate_local(Xd[W + i])
+            ev1[i].record()
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+    launches = _lib.lib.gpbt_launch_count() - launches0
+    dev_ms = maxr(sum(a.elapsed_time(b) for a, b in zip(ev0, ev1)))
+    value = world * N * K / (dev_ms * 1e-3)
+    lp_check = out[:N].cpu().numpy()
+
+    # ---- end-to-end leg: host buffers in, host result out ---------------------------------
+    lp_host = torch.empty(world * N, dtype=torch.float64).pin_memory()
+
+    def e2e_step(i):
+        if world == 1:
+            return chain.log_target(Xh[i].numpy(), -np.inf, path=args.path)      # gpbt_log_posterior_host
+        xd = Xh[i].to(dev, non_blocking=True)
+        lp_host.copy_(ev.evaluate_local(xd), non_blocking=True)
+        torch.cuda.synchronize()
+        return lp_host.numpy()
+
+    for i in range(W):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        e2e_out = e2e_step(W + i)
+    barrier()
+    e2e_s = maxr(time.perf_counter() - t0)
+    e2e_value = world * N * K / e2e_s
+
+    # ---- dominant kernel alone: (a) pc_predict ---------------------------------------------
+    de = DeviceEmulator(states[0])
+    for i in range(3):
+        de.pc_predict_device(Xd[i % nb])
+    torch.cuda.synchronize()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = max(K, 10)
+    a0.record()
+    for i in range(reps):
+        de.pc_predict_device(Xd[i % nb])
+    a1.record()
+    torch.cuda.synchronize()
+    ka_ms = a0.elapsed_time(a1) / reps
+    fl = flops_pc_predict(SHAPE["p"], SHAPE["n"], SHAPE["q"]) * N
+    achieved = fl / (ka_ms * 1e-3) / 1e12
+
+    line = None
+    if rank == 0:
+        # FP64 roofline denominator: cuBLAS DGEMM, measured here
+        n = 8192 if args.dgemm else 0
+        peak, peak_src = 35.45, "profiles/r01_dgemm_peak.json (cuBLAS DGEMM 8192^3 on this pool)"
+        if n:
+            A = torch.randn(n, n, dtype=torch.float64, device=dev)
+            B = torch.randn(n, n, dtype=torch.float64, device=dev)
+            (A @ B)
+            torch.cuda.synchronize()
+            best = 1e9
+            for _ in range(3):
+                b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                b0.record(); (A @ B); b1.record(); torch.cuda.synchronize()
+                best = min(best, b0.elapsed_time(b1))
+            peak, peak_src = 2 * n ** 3 / best / 1e9, "cuBLAS DGEMM 8192^3 (torch.matmul float64) measured in this run"
+            del A, B
+        # dense path ((a) -> (b) cov in HBM -> (c)), reported separately
+        dense = None
+        if args.dense_steps > 0:
+            Nd = args.dense_walkers
+            chain.log_target_device(Xd[0][:Nd], -np.inf, path="dense")
+            torch.cuda.synchronize()
+            d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            d0.record()
+            for i in range(args.dense_steps):
+                lpd = chain.log_target_device(Xd[i % nb][:Nd], -np.inf, path="dense")
+            d1.record()
+            torch.cuda.synchronize()
+            dms = d0.elapsed_time(d1) / args.dense_steps
+            ref = chain.log_target_device(Xd[(args.dense_steps - 1) % nb][:Nd], -np.inf, path="lowrank")
+            fin = torch.isfinite(ref)
+            dense = {"value": Nd / (dms * 1e-3), "unit": UNIT, "walkers": Nd, "ms_per_step": dms,
+                     "max_abs_diff_vs_lowrank": float((lpd[fin] - ref[fin]).abs().max().item())}
+        cpu = None
+        if world == 1 and args.cpu_rows > 0:
+            rate, dt = cpu_port_rate(g, sts, args.cpu_rows)
+            # parity spot check of the timed GPU output against the oracle on the same rows
+            from oracle import gp_oracle as orc
+            rows = 64
+            want = orc.log_posterior(sts, Xh[W + K - 1][:rows].numpy(), g["lo"], g["hi"], g["y_exp"], g["cov_exp"])
+            fin = np.isfinite(want)
+            cpu = {"value": rate, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                   "sample": "%d walkers of the same workload in chunks of 128 rows, %.1f s, NumPy/SciPy oracle port" % (args.cpu_rows, dt),
+                   "max_abs_diff_gpu_vs_oracle": float(np.max(np.abs(lp_check[:rows][fin] - want[fin])))}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "walkers_per_gpu_per_step": N, "path": args.path,
+                       "state": "hyper-parameters trained by the reference (tests/golden/c2_rbf.npz)",
+                       "l2": "256 MB flush between timed steps, outside the CUDA events",
+                       "collective": "all-gather of lp (8 B/walker)" if world > 1 else "none"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N * p * 8,
+                    "d2h_bytes_per_step": world * N * 8, "ms_per_step": 1e3 * e2e_s / K},
+            "gpu_launches": int(launches),
+            "wall_ms_per_step_incl_flush": 1e3 * t_wall / K,
+            "clocks": clk.summary(),
+            "roofline": {"kernel": "pc_predict_kernel (a)", "bound": "tensor", "achieved": achieved, "peak": peak,
+                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "ms_per_launch": ka_ms,
+                         "algorithmic_flops_per_eval": flops_pc_predict(SHAPE["p"], SHAPE["n"], SHAPE["q"]),
+                         "dtype": "FP64 DMMA.8x8x4 + DFMA (one shared pipe, 37.1 TFLOP/s DMMA issue peak measured)"},
+            "cpu_baseline": cpu,
+            "dense_path": dense,
+        }
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--walkers", type=int, default=4096, help="walkers per GPU per step")
+    ap.add_argument("--path", default="auto", choices=["auto", "lowrank", "dense"])
+    ap.add_argument("--cpu-rows", type=int, default=None, help="rows of the CPU-baseline sample")
+    ap.add_argument("--dense-steps", type=int, default=3)
+    ap.add_argument("--dense-walkers", type=int, default=2048)
+    ap.add_argument("--no-dgemm", dest="dgemm", action="store_false")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        if args.cpu_rows is None:
+            args.cpu_rows = 512
+        run_reference(args)
+    else:
+        if args.cpu_rows is None:
+            args.cpu_rows = 2048
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

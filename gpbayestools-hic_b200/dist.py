@@ -1,0 +1,78 @@
+"""
+Multi-GPU evaluation: walkers shard across the GPUs of one box, one process per GPU
+(torch.distributed, NCCL over NVLink/NVSwitch).  Rows are independent (src/mcmc.py:293,
+src/emulator.py:584), so the only collective on the data path is the all-gather of the per-walker
+log-posteriors (8 bytes per walker); emulator state is replicated on every GPU at load time.
+
+The evaluator is a callable so the partition / gather logic can be exercised on CPU with gloo
+(tests/test_dist_cpu.py); on a GPU box it is DeviceChain.log_target_device.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_bounds(N, world, rank):
+    """Contiguous row block [lo, hi) of rank `rank`: ceil(N/world) rows each, the tail may be
+    short or empty."""
+    per = -(-N // world) if N > 0 else 0
+    lo = min(N, rank * per)
+    return lo, min(N, lo + per), per
+
+
+class ShardedEvaluator:
+    def __init__(self, eval_fn, device, group=None):
+        """eval_fn(X_local [n_local, p] tensor on `device`) -> lp_local [n_local] float64 tensor."""
+        import torch.distributed as dist
+        self.eval_fn = eval_fn
+        self.device = device
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def gather_shards(self, lp_local, per):
+        """all-gather equally sized (padded) shards -> [world * per]"""
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return lp_local
+        if lp_local.shape[0] != per:
+            pad = torch.zeros(per, dtype=lp_local.dtype, device=lp_local.device)
+            pad[:lp_local.shape[0]] = lp_local
+            lp_local = pad
+        out = torch.empty(self.world * per, dtype=lp_local.dtype, device=lp_local.device)
+        dist.all_gather_into_tensor(out, lp_local.contiguous(), group=self.group)
+        return out
+
+    def evaluate_local(self, X_local):
+        """Weak-scaling form: every rank already holds its own rows; returns the gathered vector
+        [world * n_local] (all ranks must pass the same n_local)."""
+        lp = self.eval_fn(X_local)
+        return self.gather_shards(lp, X_local.shape[0])
+
+    def evaluate(self, X_host, src=0):
+        """Sampler form: rank `src` holds X [N, p] (others may pass None or the same array); X is
+        broadcast, each rank evaluates its row block, the result is all-gathered and returned as a
+        NumPy array [N] on every rank."""
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            X_d = torch.from_numpy(np.ascontiguousarray(X_host, dtype=np.float64)).to(self.device, non_blocking=True)
+            return self.eval_fn(X_d).cpu().numpy()
+        shape = torch.zeros(2, dtype=torch.int64, device=self.device)
+        if self.rank == src:
+            X_host = np.ascontiguousarray(np.array(X_host, dtype=np.float64, ndmin=2))
+            shape[0], shape[1] = X_host.shape
+        dist.broadcast(shape, src=src, group=self.group)
+        N, p = int(shape[0]), int(shape[1])
+        if self.rank == src:
+            X_d = torch.from_numpy(X_host).to(self.device)
+        else:
+            X_d = torch.empty((N, p), dtype=torch.float64, device=self.device)
+        dist.broadcast(X_d, src=src, group=self.group)
+        lo, hi, per = shard_bounds(N, self.world, self.rank)
+        if hi > lo:
+            lp_local = self.eval_fn(X_d[lo:hi].contiguous())
+        else:
+            lp_local = torch.empty(0, dtype=torch.float64, device=self.device)
+        return self.gather_shards(lp_local, per)[:N].cpu().numpy()

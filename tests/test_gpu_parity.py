@@ -55,8 +55,10 @@ def test_emulator_predict(case):
         mean0 = emu.predict(Xin[:256], return_cov=False)
         assert rel_err(mean0, g["e%d_mean0" % e]) <= REL, name
         # scalar extra_std (the reference's default 0 breaks on NumPy 2; ours must not)
+        # (a 4-row call uses a narrower walker tile than the 256-row one: same values up to
+        # summation order)
         m1 = emu.predict(Xin[:4], return_cov=False, extra_std=0)
-        assert np.array_equal(m1, mean0[:4])
+        assert rel_err(m1, mean0[:4]) <= 1e-12
 
 
 def test_chain_predict_and_mvn(case):
