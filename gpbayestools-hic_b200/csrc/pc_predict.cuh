@@ -45,75 +45,149 @@ __host__ __device__ constexpr int kt_swizzle(int k) { return (((k >> 2) & 3) << 
 
 constexpr int kPcThreads = 256;
 constexpr int kPcWarps = kPcThreads / kWarp;
-constexpr int kRowBlock = 32;  // rows of W per warp task
-constexpr int kKChunk = 16;    // k extent of one A-fragment fetch (two 16-byte loads per m8 block)
+constexpr int kRowBlock = 32;   // rows of W per warp task
+constexpr int kKChunk = 16;     // k extent of one A-fragment fetch (two 16-byte loads per m8 block)
+constexpr int kXsRows = 128;    // rows of the scaled design staged per TMA bulk copy
+constexpr int kXsStages = 2;
 
 template <int TW>
 constexpr size_t pc_predict_smem_bytes(int n_pad, int p_pad) {
-  return sizeof(double) * ((size_t)n_pad * TW + (size_t)p_pad * TW + 2 * (size_t)kPcWarps * TW);
+  return sizeof(double) * ((size_t)n_pad * TW + (size_t)kXsStages * kXsRows * p_pad + (size_t)p_pad * TW +
+                           2 * (size_t)kPcWarps * TW) + 64;
+}
+
+// ---- TMA bulk copy (global -> shared) completing on an mbarrier --------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n .reg .pred p;\n WAIT_%=:\n"
+      " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      " @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// A fragments of one k chunk: lane (g, t) holds W[i0 + 8mb + g][16kc + 4t .. 16kc + 4t + 3]
+template <int MB0>
+__device__ __forceinline__ void load_a(double (&a)[4][4], const double* __restrict__ Wrow, int n_pad, int kc) {
+  const double* base = Wrow + kc * kKChunk;
+#pragma unroll
+  for (int mb = MB0; mb < 4; mb++) {
+    const double2 lo = ldg2(base + (size_t)(8 * mb) * n_pad);
+    const double2 hi = ldg2(base + (size_t)(8 * mb) * n_pad + 2);
+    a[mb][0] = lo.x; a[mb][1] = lo.y; a[mb][2] = hi.x; a[mb][3] = hi.y;
+  }
+}
+
+// acc[mb][nt] += W-chunk * Kt-chunk for m8 blocks mb >= MB0.  Logical k slot t of step s is the
+// actual column k0 + 4t + s: the same permutation is applied to the A and B operands.
+template <int TW, int MB0>
+__device__ __forceinline__ void mma_chunk(double (&acc)[4][TW / 8][2], const double (&a)[4][4],
+                                          const double* Kt, int k0, int g, int t) {
+  constexpr int NT = TW / 8;
+#pragma unroll
+  for (int s = 0; s < 4; s++) {
+    const int k = k0 + 4 * t + s;
+    const double* row = Kt + (size_t)k * TW;
+    const int swz = kt_swizzle<TW>(k);
+    double b[NT];
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) b[nt] = row[(8 * nt + g) ^ swz];
+#pragma unroll
+    for (int mb = MB0; mb < 4; mb++)
+#pragma unroll
+      for (int nt = 0; nt < NT; nt++) dmma884(acc[mb][nt][0], acc[mb][nt][1], a[mb][s], b[nt]);
+  }
 }
 
 template <int TW, int KIND>
 __global__ void __launch_bounds__(kPcThreads, 1) pc_predict_kernel(const PcPredictParams prm) {
   constexpr int NT = TW / 8;  // n8 tiles across the walker dimension
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* Kt = reinterpret_cast<double*>(smem_raw);      // [n_pad][TW] swizzled
-  double* xs = Kt + (size_t)prm.n_pad * TW;              // [p_pad][TW]
-  double* red_mean = xs + (size_t)prm.p_pad * TW;        // [warps][TW]
-  double* red_ssq = red_mean + kPcWarps * TW;            // [warps][TW]
+  static_assert(TW == 8 || TW == 16 || TW == 32, "TW must be 8, 16 or 32");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int p = prm.p, p_pad = prm.p_pad, n = prm.n, n_pad = prm.n_pad;
+  double* Kt = reinterpret_cast<double*>(smem_raw);                 // [n_pad][TW] swizzled
+  double* xst = Kt + (size_t)n_pad * TW;                            // [stages][kXsRows][p_pad]
+  double* xs = xst + (size_t)kXsStages * kXsRows * p_pad;           // [p_pad/2][TW][2]
+  double* red_mean = xs + (size_t)p_pad * TW;                       // [warps][TW]
+  double* red_ssq = red_mean + kPcWarps * TW;                       // [warps][TW]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(red_ssq + kPcWarps * TW);  // [stages]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int j = blockIdx.y;
   const int64_t w0 = (int64_t)blockIdx.x * TW;
-  const int p = prm.p, p_pad = prm.p_pad, n = prm.n, n_pad = prm.n_pad;
+  const double* __restrict__ Xs_j = prm.Xs + (size_t)j * n_pad * p_pad;
+  const int n_xchunk = (n_pad + kXsRows - 1) / kXsRows;
+  auto chunk_bytes = [&](int c) { return (uint32_t)(min(kXsRows, n_pad - c * kXsRows) * p_pad * sizeof(double)); };
 
-  // ---- stage the scaled walker tile: xs[d][w] = X[w0+w][d] / ell_j[d] (true division, as
-  //      sklearn's X / length_scale) ---------------------------------------------------------
+  // ---- TMA: first two chunks of the scaled design X_train / ell_j into shared memory ---------
+  if (tid == 0) {
+    for (int s = 0; s < kXsStages; s++) mbar_init(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int c = 0; c < kXsStages && c < n_xchunk; c++) {
+      mbar_expect_tx(&bars[c], chunk_bytes(c));
+      tma_bulk_g2s(xst + (size_t)c * kXsRows * p_pad, Xs_j + (size_t)c * kXsRows * p_pad, chunk_bytes(c), &bars[c]);
+    }
+  }
+  // ---- the scaled walker tile: xs[d/2][w] = (x_d, x_d+1) / ell_j (true division, as sklearn's
+  //      X / length_scale) ------------------------------------------------------------------
   for (int idx = tid; idx < p_pad * TW; idx += kPcThreads) {
     const int d = idx / TW, w = idx - d * TW;
     double v = 0.0;
     if (d < p && w0 + w < prm.N) v = prm.X[(w0 + w) * p + d] / prm.ell[(size_t)j * p_pad + d];
-    xs[idx] = v;
+    xs[((size_t)(d >> 1) * TW + w) * 2 + (d & 1)] = v;
   }
   __syncthreads();
 
   // ---- phase 1: Kt and the mean ------------------------------------------------------------
   const double cj = prm.c[j];
-  const double* __restrict__ Xs_j = prm.Xs + (size_t)j * n_pad * p_pad;
   const double* __restrict__ alpha_j = prm.alpha + (size_t)j * n_pad;
   {
-    constexpr int WPR = TW / 32 > 0 ? TW / 32 : 1;  // warps needed to cover one k row (TW=32 -> 1)
-    static_assert(TW == 8 || TW == 16 || TW == 32 || TW == 64, "TW must be 8, 16, 32 or 64");
-    constexpr int LW = TW < 32 ? TW : 32;           // walkers covered by one warp pass
-    constexpr int KPW = 32 / LW;                    // k rows handled per warp pass (TW<32)
+    constexpr int LW = TW < 32 ? TW : 32;  // walkers covered by one warp pass
+    constexpr int KPW = 32 / LW;           // k rows handled per warp pass (TW < 32)
     constexpr int UNR = 4;
-    const int wl = lane % LW;                       // walker within tile (first slab)
-    const int ksub = lane / LW;                     // which of the KPW rows this lane takes
-    double msum[WPR];
-#pragma unroll
-    for (int s = 0; s < WPR; s++) msum[s] = 0.0;
-    // rows are dealt to warps in groups of UNR*KPW for ILP
-    for (int kb = warp * UNR * KPW; kb < n_pad; kb += kPcWarps * UNR * KPW) {
-#pragma unroll
-      for (int s = 0; s < WPR; s++) {
-        const int w = wl + 32 * s;
+    const int w = lane % LW;               // walker within the tile
+    const int ksub = lane / LW;            // which of the KPW rows this lane takes
+    const double2* xs2 = reinterpret_cast<const double2*>(xs);
+    double msum = 0.0;
+    for (int c = 0; c < n_xchunk; c++) {
+      const int stage = c % kXsStages;
+      const double* xc = xst + (size_t)stage * kXsRows * p_pad;
+      const int rows_c = min(kXsRows, n_pad - c * kXsRows);
+      mbar_wait(&bars[stage], (c / kXsStages) & 1);
+      // rows of this chunk are dealt to warps in groups of UNR*KPW for ILP
+      for (int rb = warp * UNR * KPW; rb < rows_c; rb += kPcWarps * UNR * KPW) {
         double acc[UNR];
+        const double* xr[UNR];
 #pragma unroll
-        for (int u = 0; u < UNR; u++) acc[u] = 0.0;
+        for (int u = 0; u < UNR; u++) {
+          acc[u] = 0.0;
+          xr[u] = xc + (size_t)min(rb + u * KPW + ksub, rows_c - 1) * p_pad;
+        }
+#pragma unroll 3
         for (int d = 0; d < p_pad; d += 2) {
-          const double x0 = xs[d * TW + w], x1 = xs[(d + 1) * TW + w];
+          const double2 x = xs2[(d >> 1) * TW + w];
 #pragma unroll
           for (int u = 0; u < UNR; u++) {
-            const int k = min(kb + u * KPW + ksub, n_pad - 1);
-            const double2 t = ldg2(Xs_j + (size_t)k * p_pad + d);
-            const double e0 = x0 - t.x, e1 = x1 - t.y;
+            const double2 tr = *reinterpret_cast<const double2*>(xr[u] + d);
+            const double e0 = x.x - tr.x, e1 = x.y - tr.y;
             acc[u] = fma(e0, e0, acc[u]);
             acc[u] = fma(e1, e1, acc[u]);
           }
         }
 #pragma unroll
         for (int u = 0; u < UNR; u++) {
-          const int k = kb + u * KPW + ksub;
+          const int kl = rb + u * KPW + ksub;
+          const int k = c * kXsRows + kl;
           double kv;
           if (KIND == 0) {
             kv = cj * exp(-0.5 * acc[u]);
@@ -122,22 +196,25 @@ __global__ void __launch_bounds__(kPcThreads, 1) pc_predict_kernel(const PcPredi
             kv = cj * ((1.0 + r) * exp(-r));
           }
           if (k >= n) kv = 0.0;
-          if (k < n_pad) {
+          if (kl < rows_c) {
             Kt[(size_t)k * TW + (w ^ kt_swizzle<TW>(k))] = kv;
-            msum[s] = fma(kv, alpha_j[k], msum[s]);
+            msum = fma(kv, alpha_j[k], msum);
           }
         }
       }
+      __syncthreads();  // every warp is done with this stage
+      if (tid == 0 && c + kXsStages < n_xchunk) {
+        const int cn = c + kXsStages;
+        mbar_expect_tx(&bars[stage], chunk_bytes(cn));
+        tma_bulk_g2s(xst + (size_t)stage * kXsRows * p_pad, Xs_j + (size_t)cn * kXsRows * p_pad, chunk_bytes(cn),
+                     &bars[stage]);
+      }
     }
     // combine the KPW partial sums that belong to the same walker, then park per-warp partials
-#pragma unroll
-    for (int s = 0; s < WPR; s++) {
-      double v = msum[s];
-      for (int o = LW; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane < LW) red_mean[warp * TW + wl + 32 * s] = v;
-    }
+    for (int o = LW; o < 32; o <<= 1) msum += __shfl_xor_sync(0xffffffffu, msum, o);
+    if (lane < LW) red_mean[warp * TW + w] = msum;
   }
-  __syncthreads();
+  // (the trailing __syncthreads of the last chunk also publishes Kt)
 
   // ---- phase 2: ssq[w] = sum_i (sum_{k<=i} W[i][k] K[w][k])^2 on the FP64 tensor pipe ---------
   const double* __restrict__ W_j = prm.W + (size_t)j * n_pad * n_pad;
@@ -147,61 +224,35 @@ __global__ void __launch_bounds__(kPcThreads, 1) pc_predict_kernel(const PcPredi
 #pragma unroll
   for (int nt = 0; nt < NT; nt++) ssq[nt][0] = ssq[nt][1] = 0.0;
 
-  // task list of this warp: pairs (r, nrb-1-r) for r = warp, warp + kPcWarps, ...
+  // task list of this warp: pairs of row blocks (r, nrb-1-r) for r = warp, warp + kPcWarps, ...
   for (int pr = warp; 2 * pr < nrb; pr += kPcWarps) {
 #pragma unroll 1
     for (int half = 0; half < 2; half++) {
       const int rb = half == 0 ? pr : nrb - 1 - pr;
       if (half == 1 && rb == pr) break;
       const int i0 = rb * kRowBlock;
+      const double* __restrict__ Wrow = W_j + (size_t)(i0 + g) * n_pad + 4 * t;
       double acc[4][NT][2];
 #pragma unroll
       for (int mb = 0; mb < 4; mb++)
 #pragma unroll
         for (int nt = 0; nt < NT; nt++) acc[mb][nt][0] = acc[mb][nt][1] = 0.0;
-
-      const int nchunk = (i0 + kRowBlock) / kKChunk;  // k chunks 0 .. nchunk-1 touch rows <= i0+31
-      // A fragments for one chunk: lane holds W[i0 + 8mb + g][k0 + 4t .. k0 + 4t + 3]
-      double a_cur[4][4], a_nxt[4][4];
-      auto load_a = [&](double (&a)[4][4], int kc) {
-        const double* base = W_j + (size_t)(i0 + g) * n_pad + kc * kKChunk + 4 * t;
-#pragma unroll
-        for (int mb = 0; mb < 4; mb++) {
-          const double2 lo = ldg2(base + (size_t)(8 * mb) * n_pad);
-          const double2 hi = ldg2(base + (size_t)(8 * mb) * n_pad + 2);
-          a[mb][0] = lo.x; a[mb][1] = lo.y; a[mb][2] = hi.x; a[mb][3] = hi.y;
-        }
-      };
-      load_a(a_cur, 0);
+      // k chunks 0 .. 2rb+1 touch this row block; they are consumed in pairs from two register
+      // buffers (no copies, loads run one full chunk ahead of their use)
+      double a0[4][4], a1[4][4];
+      load_a<0>(a0, Wrow, n_pad, 0);
 #pragma unroll 1
-      for (int kc = 0; kc < nchunk; kc++) {
-        if (kc + 1 < nchunk) load_a(a_nxt, kc + 1);
-        const int k0 = kc * kKChunk;
-        // m8 blocks whose rows all lie above this chunk's columns hold only zeros of the
-        // (strictly upper) triangle: skip them.  rows of block mb: i0+8mb .. i0+8mb+7
-        const int mb_first = (k0 > i0) ? ((k0 - i0) >> 3) : 0;
-#pragma unroll
-        for (int s = 0; s < 4; s++) {
-          // logical k slot t of step s  <->  actual k = k0 + 4t + s  (same permutation for A and B)
-          const int k = k0 + 4 * t + s;
-          double b[NT];
-#pragma unroll
-          for (int nt = 0; nt < NT; nt++) b[nt] = Kt[(size_t)k * TW + ((8 * nt + g) ^ kt_swizzle<TW>(k))];
-#pragma unroll
-          for (int mb = 0; mb < 4; mb++) {
-            if (mb >= mb_first) {
-#pragma unroll
-              for (int nt = 0; nt < NT; nt++) dmma884(acc[mb][nt][0], acc[mb][nt][1], a_cur[mb][s], b[nt]);
-            }
-          }
-        }
-        if (kc + 1 < nchunk) {
-#pragma unroll
-          for (int mb = 0; mb < 4; mb++)
-#pragma unroll
-            for (int s = 0; s < 4; s++) a_cur[mb][s] = a_nxt[mb][s];
-        }
+      for (int cp = 0; cp < rb; cp++) {
+        load_a<0>(a1, Wrow, n_pad, 2 * cp + 1);
+        mma_chunk<TW, 0>(acc, a0, Kt, (2 * cp) * kKChunk, g, t);
+        load_a<0>(a0, Wrow, n_pad, 2 * cp + 2);
+        mma_chunk<TW, 0>(acc, a1, Kt, (2 * cp + 1) * kKChunk, g, t);
       }
+      // last pair: chunk 2rb holds the diagonal; in chunk 2rb+1 the m8 blocks 0 and 1 (rows
+      // i0 .. i0+15) lie strictly above the diagonal and are skipped
+      load_a<2>(a1, Wrow, n_pad, 2 * rb + 1);
+      mma_chunk<TW, 0>(acc, a0, Kt, (2 * rb) * kKChunk, g, t);
+      mma_chunk<TW, 2>(acc, a1, Kt, (2 * rb + 1) * kKChunk, g, t);
 #pragma unroll
       for (int mb = 0; mb < 4; mb++)
 #pragma unroll
