@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -69,7 +70,7 @@ int max_optin_smem() {
 
 struct gpbt_emulator {
   int p, p_pad, n, n_pad, q, q_pad, m, m_ld, kind, flags, device;
-  double *Xs, *ell, *c, *sn, *alpha, *W, *A, *mu, *scale, *Ctrunc;
+  double *Xs, *ell, *c, *sn, *W, *A, *mu, *scale, *Ctrunc;
 };
 
 struct gpbt_chain {
@@ -120,12 +121,17 @@ extern "C" int gpbt_emulator_create(gpbt_emulator_t* out, int p, int n, int q, i
   cudaGetDevice(&e->device);
   const int P = e->p_pad, NP = e->n_pad;
 
+  // staged design rows: (X_train[i] / ell_j  [true division, as sklearn's X / length_scale],
+  // zero pad to p_pad, alpha_j[i], 0)
   std::vector<double> h;
-  h.assign((size_t)q * NP * P, 0.0);
+  const int XR = P + 2;
+  h.assign((size_t)q * NP * XR, 0.0);
   for (int j = 0; j < q; j++)
-    for (int i = 0; i < n; i++)
-      for (int d = 0; d < p; d++)
-        h[((size_t)j * NP + i) * P + d] = Xtr[(size_t)i * p + d] / ell[(size_t)j * p + d];
+    for (int i = 0; i < n; i++) {
+      double* row = &h[((size_t)j * NP + i) * XR];
+      for (int d = 0; d < p; d++) row[d] = Xtr[(size_t)i * p + d] / ell[(size_t)j * p + d];
+      row[P] = alpha[(size_t)j * n + i];
+    }
   if (int r = upload(&e->Xs, h)) return r;
   h.assign((size_t)q * P, 1.0);
   for (int j = 0; j < q; j++)
@@ -135,9 +141,6 @@ extern "C" int gpbt_emulator_create(gpbt_emulator_t* out, int p, int n, int q, i
   if (int r = upload(&e->c, h)) return r;
   h.assign(sn, sn + q);
   if (int r = upload(&e->sn, h)) return r;
-  h.assign((size_t)q * NP, 0.0);
-  for (int j = 0; j < q; j++) memcpy(&h[(size_t)j * NP], alpha + (size_t)j * n, n * sizeof(double));
-  if (int r = upload(&e->alpha, h)) return r;
   h.assign((size_t)q * NP * NP, 0.0);
   for (int j = 0; j < q; j++)
     for (int i = 0; i < n; i++)
@@ -162,7 +165,7 @@ extern "C" int gpbt_emulator_create(gpbt_emulator_t* out, int p, int n, int q, i
 
 extern "C" int gpbt_emulator_destroy(gpbt_emulator_t e) {
   if (!e) return 0;
-  double* ptrs[] = {e->Xs, e->ell, e->c, e->sn, e->alpha, e->W, e->A, e->mu, e->scale, e->Ctrunc};
+  double* ptrs[] = {e->Xs, e->ell, e->c, e->sn, e->W, e->A, e->mu, e->scale, e->Ctrunc};
   for (double* p : ptrs)
     if (p) cudaFree(p);
   delete e;
@@ -174,34 +177,57 @@ extern "C" int gpbt_emulator_destroy(gpbt_emulator_t e) {
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-template <int TW, int KIND>
+template <int TW, int KIND, int P2>
 int launch_pc_predict(const PcPredictParams& prm, cudaStream_t st) {
   const size_t smem = pc_predict_smem_bytes<TW>(prm.n_pad, prm.p_pad);
   static size_t configured = 0;
   if (smem > configured) {
-    CU(cudaFuncSetAttribute(pc_predict_kernel<TW, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(pc_predict_kernel<TW, KIND, P2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   dim3 grid((unsigned)((prm.N + TW - 1) / TW), (unsigned)prm.q);
-  pc_predict_kernel<TW, KIND><<<grid, kPcThreads, smem, st>>>(prm);
+  pc_predict_kernel<TW, KIND, P2><<<grid, kPcThreads, smem, st>>>(prm);
   LAUNCH_CHECK();
   return 0;
 }
 
+// compile-time parameter-count specialisations (p_pad = 2 * P2 <= 24); generic p otherwise
+template <int TW, int KIND>
+int launch_pc_predict_p(const PcPredictParams& prm, cudaStream_t st) {
+  switch (prm.p_pad / 2) {
+#define GPBT_P2(P) case P: return launch_pc_predict<TW, KIND, P>(prm, st);
+    GPBT_P2(1) GPBT_P2(2) GPBT_P2(3) GPBT_P2(4) GPBT_P2(5) GPBT_P2(6)
+    GPBT_P2(7) GPBT_P2(8) GPBT_P2(9) GPBT_P2(10) GPBT_P2(11) GPBT_P2(12)
+#undef GPBT_P2
+    default: return launch_pc_predict<TW, KIND, 0>(prm, st);
+  }
+}
+
+// Walker-tile width.  16 walkers x 2 resident CTAs per SM is the default for large batches: one
+// CTA's phase 1 (distance + exp, issue/latency bound) overlaps the other's phase 2 (DMMA bound),
+// measured 0.86 ms vs 0.94 ms for one 32-wide CTA per SM at config 2.  32 is used when two 16-wide
+// CTAs do not fit in shared memory; 8 for small batches (more CTAs, lower latency).
+// GPBT_PC_TILE=8|16|32 overrides (tuning / tests).
 template <int KIND>
 int dispatch_pc_predict(const PcPredictParams& prm, cudaStream_t st) {
   const size_t limit = (size_t)max_optin_smem();
-  // widest walker tile that fits in shared memory, narrowed while the grid would leave SMs idle
-  int tw = 32;
-  if (pc_predict_smem_bytes<32>(prm.n_pad, prm.p_pad) > limit) tw = 16;
+  const size_t per_sm = 228 * 1024 - 2048;
+  int tw = 16;
+  if (2 * (pc_predict_smem_bytes<16>(prm.n_pad, prm.p_pad) + 1024) > per_sm &&
+      pc_predict_smem_bytes<32>(prm.n_pad, prm.p_pad) <= limit)
+    tw = 32;
   if (tw == 16 && pc_predict_smem_bytes<16>(prm.n_pad, prm.p_pad) > limit) tw = 8;
   if (tw == 8 && pc_predict_smem_bytes<8>(prm.n_pad, prm.p_pad) > limit)
     return fail(GPBT_ESHAPE, "pc_predict: n = %d design points do not fit in shared memory", prm.n);
   const int64_t want = 2 * 148;
   while (tw > 8 && ((prm.N + tw - 1) / tw) * prm.q < want) tw >>= 1;
-  if (tw == 32) return launch_pc_predict<32, KIND>(prm, st);
-  if (tw == 16) return launch_pc_predict<16, KIND>(prm, st);
-  return launch_pc_predict<8, KIND>(prm, st);
+  if (const char* env = getenv("GPBT_PC_TILE")) {
+    const int v = atoi(env);
+    if (v == 8 || v == 16 || v == 32) tw = v;
+  }
+  if (tw == 32) return launch_pc_predict_p<32, KIND>(prm, st);
+  if (tw == 16) return launch_pc_predict_p<16, KIND>(prm, st);
+  return launch_pc_predict<8, KIND, 0>(prm, st);
 }
 
 int run_pc_predict(gpbt_emulator_t e, const double* X, const double* extra, double* zm, double* zv,
@@ -209,7 +235,7 @@ int run_pc_predict(gpbt_emulator_t e, const double* X, const double* extra, doub
   if (N <= 0) return 0;
   PcPredictParams prm;
   prm.X = X; prm.extra = extra; prm.Xs = e->Xs; prm.ell = e->ell; prm.c = e->c; prm.sn = e->sn;
-  prm.alpha = e->alpha; prm.W = e->W; prm.z_mean = zm; prm.z_var = zv; prm.ldz = ldz; prm.N = N;
+  prm.W = e->W; prm.z_mean = zm; prm.z_var = zv; prm.ldz = ldz; prm.N = N;
   prm.p = e->p; prm.p_pad = e->p_pad; prm.n = e->n; prm.n_pad = e->n_pad; prm.q = e->q;
   return e->kind == GPBT_KERNEL_RBF ? dispatch_pc_predict<0>(prm, st) : dispatch_pc_predict<1>(prm, st);
 }
@@ -287,6 +313,22 @@ __global__ void extra_std_kernel(const double* __restrict__ X, int p, int64_t N,
 }
 
 }  // namespace
+
+__global__ void debug_exp_neg_kernel(const double* __restrict__ x, double* __restrict__ y, int64_t n) {
+  __shared__ double2 tab[64];
+  if (threadIdx.x < 64) tab[threadIdx.x] = kExpTable[threadIdx.x];
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = exp_neg(x[i], tab);
+}
+
+extern "C" int gpbt_debug_exp_neg(const double* x, double* y, int64_t n, void* stream) {
+  if (!x || !y || n < 0) return fail(GPBT_EINVAL, "gpbt_debug_exp_neg: bad argument");
+  if (n == 0) return 0;
+  debug_exp_neg_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, y, n);
+  LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int gpbt_pc_predict(gpbt_emulator_t emu, const double* X, const double* extra, double* zm,
                                double* zv, int64_t ldz, int64_t N, void* stream) {

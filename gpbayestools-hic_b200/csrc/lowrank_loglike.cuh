@@ -37,20 +37,31 @@ constexpr int kLrWarps = 4;
 
 __host__ __device__ inline int lowrank_stride(int Q) { return Q | 1; }
 inline size_t lowrank_smem_bytes(int Q) {
-  return sizeof(double) * ((size_t)Q * Q + (size_t)kLrWarps * ((size_t)Q * lowrank_stride(Q) + 3 * (size_t)Q));
+  return sizeof(double) * (2 * (size_t)Q * lowrank_stride(Q) +
+                           (size_t)kLrWarps * ((size_t)Q * lowrank_stride(Q) + 4 * (size_t)Q));
 }
 
+// Lanes own rows (a = lane, lane + 32, ...); S is kept column-major in shared memory
+// (S[c * ld + a]) so every per-column step is one conflict-free vector operation across the warp
+// and the loops over columns are warp-uniform.
 __global__ void __launch_bounds__(kLrWarps * 32) lowrank_loglike_kernel(const LowrankParams prm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int Q = prm.Q, ld = lowrank_stride(Q);
-  double* Rs = reinterpret_cast<double*>(smem_raw);                 // [Q][Q]
+  double* Rt = reinterpret_cast<double*>(smem_raw);  // Rt[k * ld + a] = R[a][k]   (zero for k < a)
+  double* Rr = Rt + (size_t)Q * ld;                  // Rr[a * ld + k] = R[a][k]   (row-major, broadcast reads)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* S = Rs + Q * Q + (size_t)warp * (Q * ld + 3 * Q);         // [Q][ld]
-  double* cv = S + Q * ld;                                          // [Q]
-  double* vs = cv + Q;                                              // [Q]
-  double* zs = vs + Q;                                              // [Q]
+  double* S = Rr + (size_t)Q * ld + (size_t)warp * ((size_t)Q * ld + 4 * Q);  // [Q cols][ld]
+  double* cv = S + (size_t)Q * ld;                   // [Q]
+  double* vs = cv + Q;                               // [Q]
+  double* zs = vs + Q;                               // [Q]
+  double* dg = zs + Q;                               // [Q] pivots d_b (for the log-determinant)
 
-  for (int i = threadIdx.x; i < Q * Q; i += blockDim.x) Rs[i] = prm.R[i];
+  for (int i = threadIdx.x; i < Q * Q; i += blockDim.x) {
+    const int a = i / Q, k = i - a * Q;
+    const double r = (k >= a) ? prm.R[i] : 0.0;
+    Rt[k * ld + a] = r;
+    Rr[a * ld + k] = r;
+  }
   __syncthreads();
 
   const int64_t w = (int64_t)blockIdx.x * kLrWarps + warp;
@@ -72,38 +83,41 @@ __global__ void __launch_bounds__(kLrWarps * 32) lowrank_loglike_kernel(const Lo
     vs[a] = prm.z_var[w * Q + a];
   }
   __syncwarp();
+  // c = c0 + R z ;  S[:, b] (rows a >= b) = delta_ab + sum_k R[a][k] v_k R[b][k]
   for (int a = lane; a < Q; a += 32) {
     double s = prm.c0[a];
-    for (int k = a; k < Q; k++) s = fma(Rs[a * Q + k], zs[k], s);
+    for (int k = 0; k < Q; k++) s = fma(Rt[k * ld + a], zs[k], s);
     cv[a] = s;
   }
-  // S (lower triangle) = I + R diag(v) R^T ; R upper triangular -> k runs from max(a,b) = a
-  for (int idx = lane; idx < Q * (Q + 1) / 2; idx += 32) {
-    int a = (int)((sqrt(8.0 * idx + 1.0) - 1.0) * 0.5);
-    while ((a + 1) * (a + 2) / 2 <= idx) a++;
-    while (a * (a + 1) / 2 > idx) a--;
-    const int b = idx - a * (a + 1) / 2;
-    double s = (a == b) ? 1.0 : 0.0;
-    for (int k = a; k < Q; k++) s = fma(Rs[a * Q + k] * vs[k], Rs[b * Q + k], s);
-    S[a * ld + b] = s;
+  for (int b = 0; b < Q; b++) {
+    for (int a = b + lane; a < Q; a += 32) {
+      double s = (a == b) ? 1.0 : 0.0;
+      for (int k = b; k < Q; k++) s = fma(Rt[k * ld + a], vs[k] * Rr[b * ld + k], s);
+      S[b * ld + a] = s;
+    }
   }
   __syncwarp();
 
-  // in-place Cholesky (lower), right-looking, one column per step
-  double logdet = 0.0;
+  // right-looking Cholesky, one column per step; the forward solve t = L^-1 c rides along
   bool pd = true;
+  double quad = 0.0;
   for (int b = 0; b < Q; b++) {
     const double d = S[b * ld + b];
     if (!(d > 0.0)) { pd = false; break; }
-    const double l = sqrt(d);
-    logdet += log(l);
-    const double inv = 1.0 / l;
-    for (int a = b + 1 + lane; a < Q; a += 32) S[a * ld + b] *= inv;
+    const double inv = rsqrt(d);
+    const double tb = cv[b] * inv;                   // t_b = c_b / l_bb
+    quad = fma(tb, tb, quad);
     __syncwarp();
-    if (lane == 0) S[b * ld + b] = l;  // after the barrier: every lane has read the old diagonal
     for (int a = b + 1 + lane; a < Q; a += 32) {
-      const double lab = S[a * ld + b];
-      for (int c = b + 1; c <= a; c++) S[a * ld + c] = fma(-lab, S[c * ld + b], S[a * ld + c]);
+      const double lab = S[b * ld + a] * inv;        // L[a][b]
+      S[b * ld + a] = lab;
+      cv[a] = fma(-lab, tb, cv[a]);
+    }
+    if (lane == 0) dg[b] = d;
+    __syncwarp();
+    for (int c = b + 1; c < Q; c++) {                // trailing update, column by column
+      const double lcb = S[b * ld + c];
+      for (int a = c + lane; a < Q; a += 32) S[c * ld + a] = fma(-S[b * ld + a], lcb, S[c * ld + a]);
     }
     __syncwarp();
   }
@@ -114,17 +128,11 @@ __global__ void __launch_bounds__(kLrWarps * 32) lowrank_loglike_kernel(const Lo
     }
     return;
   }
-  // forward solve t = L^-1 c (column oriented), quad = |t|^2
-  double quad = 0.0;
-  for (int b = 0; b < Q; b++) {
-    const double tb = cv[b] / S[b * ld + b];
-    quad = fma(tb, tb, quad);
-    __syncwarp();
-    for (int a = b + 1 + lane; a < Q; a += 32) cv[a] = fma(-S[a * ld + b], tb, cv[a]);
-    __syncwarp();
-  }
+  double logdet2 = 0.0;                              // sum log d_b = 2 sum log l_bb
+  for (int b = lane; b < Q; b += 32) logdet2 += log(dg[b]);
+  logdet2 = warp_sum(logdet2);
   if (lane == 0)
-    prm.lp[w] = -0.5 * (prm.s_perp + quad) - logdet - prm.logdetF_half + prm.sys_const;
+    prm.lp[w] = -0.5 * (prm.s_perp + quad) - 0.5 * logdet2 - prm.logdetF_half + prm.sys_const;
 }
 
 }  // namespace gpbt

@@ -20,17 +20,17 @@
 //            the triangular work is balanced.
 #pragma once
 #include "common.cuh"
+#include "fast_exp.cuh"
 
 namespace gpbt {
 
 struct PcPredictParams {
   const double* __restrict__ X;      // [N, p] walkers
   const double* __restrict__ extra;  // [N] extra_std or nullptr
-  const double* __restrict__ Xs;     // [q, n_pad, p_pad]  X_train / ell_j, zero padded
+  const double* __restrict__ Xs;     // [q, n_pad, p_pad + 2]  row k = (X_train[k] / ell_j, 0-pad, alpha_j[k], 0)
   const double* __restrict__ ell;    // [q, p_pad]          (pad = 1)
   const double* __restrict__ c;      // [q]
   const double* __restrict__ sn;     // [q]
-  const double* __restrict__ alpha;  // [q, n_pad] zero padded
   const double* __restrict__ W;      // [q, n_pad, n_pad] lower-triangular inverse of L_j, zero padded
   double* __restrict__ z_mean;       // [N, ldz]
   double* __restrict__ z_var;        // [N, ldz]
@@ -52,8 +52,8 @@ constexpr int kXsStages = 2;
 
 template <int TW>
 constexpr size_t pc_predict_smem_bytes(int n_pad, int p_pad) {
-  return sizeof(double) * ((size_t)n_pad * TW + (size_t)kXsStages * kXsRows * p_pad + (size_t)p_pad * TW +
-                           2 * (size_t)kPcWarps * TW) + 64;
+  return sizeof(double) * ((size_t)n_pad * TW + (size_t)kXsStages * kXsRows * (p_pad + 2) + (size_t)p_pad * TW +
+                           2 * (size_t)kPcWarps * TW) + 64 * sizeof(double2) + 64;
 }
 
 // ---- TMA bulk copy (global -> shared) completing on an mbarrier --------------------------------
@@ -109,25 +109,30 @@ __device__ __forceinline__ void mma_chunk(double (&acc)[4][TW / 8][2], const dou
   }
 }
 
-template <int TW, int KIND>
-__global__ void __launch_bounds__(kPcThreads, 1) pc_predict_kernel(const PcPredictParams prm) {
+// P2 > 0: p_pad / 2 known at compile time -- the walker's scaled coordinates stay in registers for
+// the whole of phase 1 and the distance loop is fully unrolled (only warp-uniform, broadcast shared
+// memory reads remain).  P2 == 0: generic p, coordinates re-read from shared memory.
+template <int TW, int KIND, int P2>
+__global__ void __launch_bounds__(kPcThreads, TW == 16 ? 2 : 1) pc_predict_kernel(const PcPredictParams prm) {
   constexpr int NT = TW / 8;  // n8 tiles across the walker dimension
   static_assert(TW == 8 || TW == 16 || TW == 32, "TW must be 8, 16 or 32");
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int p = prm.p, p_pad = prm.p_pad, n = prm.n, n_pad = prm.n_pad;
+  const int p = prm.p, p_pad = P2 > 0 ? 2 * P2 : prm.p_pad, n = prm.n, n_pad = prm.n_pad;
+  const int xrow = p_pad + 2;                                       // doubles per staged design row
   double* Kt = reinterpret_cast<double*>(smem_raw);                 // [n_pad][TW] swizzled
-  double* xst = Kt + (size_t)n_pad * TW;                            // [stages][kXsRows][p_pad]
-  double* xs = xst + (size_t)kXsStages * kXsRows * p_pad;           // [p_pad/2][TW][2]
+  double* xst = Kt + (size_t)n_pad * TW;                            // [stages][kXsRows][xrow]
+  double* xs = xst + (size_t)kXsStages * kXsRows * xrow;            // [p_pad/2][TW][2]
   double* red_mean = xs + (size_t)p_pad * TW;                       // [warps][TW]
   double* red_ssq = red_mean + kPcWarps * TW;                       // [warps][TW]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(red_ssq + kPcWarps * TW);  // [stages]
+  double2* etab = reinterpret_cast<double2*>(red_ssq + kPcWarps * TW);    // [64] 2^(j/64) (hi, lo)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(etab + 64);                // [stages]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int j = blockIdx.y;
   const int64_t w0 = (int64_t)blockIdx.x * TW;
-  const double* __restrict__ Xs_j = prm.Xs + (size_t)j * n_pad * p_pad;
+  const double* __restrict__ Xs_j = prm.Xs + (size_t)j * n_pad * xrow;
   const int n_xchunk = (n_pad + kXsRows - 1) / kXsRows;
-  auto chunk_bytes = [&](int c) { return (uint32_t)(min(kXsRows, n_pad - c * kXsRows) * p_pad * sizeof(double)); };
+  auto chunk_bytes = [&](int c) { return (uint32_t)(min(kXsRows, n_pad - c * kXsRows) * xrow * sizeof(double)); };
 
   // ---- TMA: first two chunks of the scaled design X_train / ell_j into shared memory ---------
   if (tid == 0) {
@@ -135,7 +140,7 @@ __global__ void __launch_bounds__(kPcThreads, 1) pc_predict_kernel(const PcPredi
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     for (int c = 0; c < kXsStages && c < n_xchunk; c++) {
       mbar_expect_tx(&bars[c], chunk_bytes(c));
-      tma_bulk_g2s(xst + (size_t)c * kXsRows * p_pad, Xs_j + (size_t)c * kXsRows * p_pad, chunk_bytes(c), &bars[c]);
+      tma_bulk_g2s(xst + (size_t)c * kXsRows * xrow, Xs_j + (size_t)c * kXsRows * xrow, chunk_bytes(c), &bars[c]);
     }
   }
   // ---- the scaled walker tile: xs[d/2][w] = (x_d, x_d+1) / ell_j (true division, as sklearn's
@@ -146,11 +151,11 @@ __global__ void __launch_bounds__(kPcThreads, 1) pc_predict_kernel(const PcPredi
     if (d < p && w0 + w < prm.N) v = prm.X[(w0 + w) * p + d] / prm.ell[(size_t)j * p_pad + d];
     xs[((size_t)(d >> 1) * TW + w) * 2 + (d & 1)] = v;
   }
+  if (tid < 64) etab[tid] = kExpTable[tid];
   __syncthreads();
 
   // ---- phase 1: Kt and the mean ------------------------------------------------------------
   const double cj = prm.c[j];
-  const double* __restrict__ alpha_j = prm.alpha + (size_t)j * n_pad;
   {
     constexpr int LW = TW < 32 ? TW : 32;  // walkers covered by one warp pass
     constexpr int KPW = 32 / LW;           // k rows handled per warp pass (TW < 32)
@@ -158,47 +163,67 @@ __global__ void __launch_bounds__(kPcThreads, 1) pc_predict_kernel(const PcPredi
     const int w = lane % LW;               // walker within the tile
     const int ksub = lane / LW;            // which of the KPW rows this lane takes
     const double2* xs2 = reinterpret_cast<const double2*>(xs);
+    double2 xreg[P2 > 0 ? P2 : 1];
+    if (P2 > 0) {
+#pragma unroll
+      for (int d2 = 0; d2 < P2; d2++) xreg[d2] = xs2[d2 * TW + w];
+    }
     double msum = 0.0;
     for (int c = 0; c < n_xchunk; c++) {
       const int stage = c % kXsStages;
-      const double* xc = xst + (size_t)stage * kXsRows * p_pad;
+      const double* xc = xst + (size_t)stage * kXsRows * xrow;
       const int rows_c = min(kXsRows, n_pad - c * kXsRows);
       mbar_wait(&bars[stage], (c / kXsStages) & 1);
       // rows of this chunk are dealt to warps in groups of UNR*KPW for ILP
       for (int rb = warp * UNR * KPW; rb < rows_c; rb += kPcWarps * UNR * KPW) {
-        double acc[UNR];
-        const double* xr[UNR];
+        double acc[UNR], acc1[UNR];
+        const double2* xr[UNR];
 #pragma unroll
         for (int u = 0; u < UNR; u++) {
-          acc[u] = 0.0;
-          xr[u] = xc + (size_t)min(rb + u * KPW + ksub, rows_c - 1) * p_pad;
+          acc[u] = acc1[u] = 0.0;
+          xr[u] = reinterpret_cast<const double2*>(xc + (size_t)min(rb + u * KPW + ksub, rows_c - 1) * xrow);
         }
-#pragma unroll 3
-        for (int d = 0; d < p_pad; d += 2) {
-          const double2 x = xs2[(d >> 1) * TW + w];
+        if (P2 > 0) {
 #pragma unroll
-          for (int u = 0; u < UNR; u++) {
-            const double2 tr = *reinterpret_cast<const double2*>(xr[u] + d);
-            const double e0 = x.x - tr.x, e1 = x.y - tr.y;
-            acc[u] = fma(e0, e0, acc[u]);
-            acc[u] = fma(e1, e1, acc[u]);
+          for (int d2 = 0; d2 < P2; d2++) {
+#pragma unroll
+            for (int u = 0; u < UNR; u++) {
+              const double2 tr = xr[u][d2];
+              const double e0 = xreg[d2].x - tr.x, e1 = xreg[d2].y - tr.y;
+              acc[u] = fma(e0, e0, acc[u]);
+              acc1[u] = fma(e1, e1, acc1[u]);
+            }
+          }
+        } else {
+          const double2* xq = xs2 + w;
+#pragma unroll 3
+          for (int d2 = 0; d2 < (p_pad >> 1); d2++) {
+            const double2 x = xq[d2 * TW];
+#pragma unroll
+            for (int u = 0; u < UNR; u++) {
+              const double2 tr = xr[u][d2];
+              const double e0 = x.x - tr.x, e1 = x.y - tr.y;
+              acc[u] = fma(e0, e0, acc[u]);
+              acc1[u] = fma(e1, e1, acc1[u]);
+            }
           }
         }
 #pragma unroll
         for (int u = 0; u < UNR; u++) {
+          const double d2sum = acc[u] + acc1[u];
           const int kl = rb + u * KPW + ksub;
           const int k = c * kXsRows + kl;
           double kv;
           if (KIND == 0) {
-            kv = cj * exp(-0.5 * acc[u]);
+            kv = cj * exp_neg(-0.5 * d2sum, etab);
           } else {
-            const double r = sqrt(acc[u]) * 1.7320508075688772;  // sqrt(3) rounded as np.sqrt(3)
-            kv = cj * ((1.0 + r) * exp(-r));
+            const double r = sqrt(d2sum) * 1.7320508075688772;  // sqrt(3) rounded as np.sqrt(3)
+            kv = cj * ((1.0 + r) * exp_neg(-r, etab));
           }
           if (k >= n) kv = 0.0;
           if (kl < rows_c) {
             Kt[(size_t)k * TW + (w ^ kt_swizzle<TW>(k))] = kv;
-            msum = fma(kv, alpha_j[k], msum);
+            msum = fma(kv, xr[u][p_pad >> 1].x, msum);   // alpha_j[k] rides in the staged row
           }
         }
       }
@@ -206,7 +231,7 @@ __global__ void __launch_bounds__(kPcThreads, 1) pc_predict_kernel(const PcPredi
       if (tid == 0 && c + kXsStages < n_xchunk) {
         const int cn = c + kXsStages;
         mbar_expect_tx(&bars[stage], chunk_bytes(cn));
-        tma_bulk_g2s(xst + (size_t)stage * kXsRows * p_pad, Xs_j + (size_t)cn * kXsRows * p_pad, chunk_bytes(cn),
+        tma_bulk_g2s(xst + (size_t)stage * kXsRows * xrow, Xs_j + (size_t)cn * kXsRows * xrow, chunk_bytes(cn),
                      &bars[stage]);
       }
     }

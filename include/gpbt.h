@@ -130,6 +130,9 @@ int gpbt_log_posterior_host(gpbt_chain_t chain, const double* X_host, double oob
 /* bytes of device workspace the chain currently holds (grows with the largest N seen)        */
 int64_t gpbt_chain_workspace_bytes(gpbt_chain_t chain);
 
+/* test hook: y[i] = the kernels' internal exp(x[i]) for x <= 0 (accuracy is pinned by a test)  */
+int gpbt_debug_exp_neg(const double* x_dev, double* y_dev, int64_t n, void* stream);
+
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches)      */
 int64_t gpbt_launch_count(void);
 

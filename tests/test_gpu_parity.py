@@ -165,3 +165,31 @@ def test_invariances():
     dense = ch.log_target(X[:500], -np.inf, path="dense")
     assert np.max(np.abs(dense - lp[:500])) <= ABS_LP
     assert ch.log_target(np.empty((0, len(g["lo"]))), -np.inf).shape == (0,)
+    # every walker-tile width of kernel (a) gives the same numbers (GPBT_PC_TILE is the tuning override)
+    import os
+    try:
+        for tile in ("8", "16", "32"):
+            os.environ["GPBT_PC_TILE"] = tile
+            assert np.max(np.abs(ch.log_target(X[:700], -np.inf) - lp[:700])) <= 1e-10, tile
+    finally:
+        os.environ.pop("GPBT_PC_TILE", None)
+
+
+def test_exp_accuracy():
+    """the kernels' branch-free exp(x), x <= 0, against numpy.exp: <= 1 ulp over the range the GP
+    kernels use, exact 1 at 0, 0 below the underflow threshold"""
+    import torch
+    from gpbt_b200 import _lib
+    rng = np.random.default_rng(1)
+    x = np.concatenate([-rng.uniform(0, 50, 400000), -rng.uniform(0, 1e-3, 50000), -rng.uniform(50, 708, 50000),
+                        np.array([0.0, -0.0, -1e-300, -708.0, -709.0, -1e4, -np.inf])])
+    xd = torch.from_numpy(x).cuda()
+    yd = torch.empty_like(xd)
+    _lib.check(_lib.lib.gpbt_debug_exp_neg(xd.data_ptr(), yd.data_ptr(), len(x), None))
+    torch.cuda.synchronize()
+    y = yd.cpu().numpy()
+    ref = np.exp(x)
+    ok = x >= -708.0
+    ulp = np.abs(y[ok] - ref[ok]) / np.spacing(ref[ok])
+    assert ulp.max() <= 1.0, ulp.max()
+    assert np.all(y[~ok] == 0.0) and y[len(x) - 7] == 1.0
