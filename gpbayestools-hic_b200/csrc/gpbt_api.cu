@@ -519,6 +519,16 @@ extern "C" int gpbt_log_posterior(gpbt_chain_t ch, const double* X, double oob_v
     prm.R = ch->R; prm.c0 = ch->c0; prm.lp = lp; prm.n_notpd = n_notpd; prm.s_perp = ch->s_perp;
     prm.logdetF_half = ch->logdetF_half; prm.oob_value = oob_value; prm.sys_const = kSysConst;
     prm.N = N; prm.p = ch->p; prm.Q = ch->Q;
+    const unsigned grid = (unsigned)((N + kLrWarps - 1) / kLrWarps);
+    if (ch->Q <= 32 && !getenv("GPBT_LOWRANK_GENERIC")) {
+      switch ((ch->Q + 3) / 4) {
+#define GPBT_Q(QP) case QP / 4: lowrank_loglike_reg_kernel<QP><<<grid, kLrWarps * 32, 0, st>>>(prm); break;
+        GPBT_Q(4) GPBT_Q(8) GPBT_Q(12) GPBT_Q(16) GPBT_Q(20) GPBT_Q(24) GPBT_Q(28) GPBT_Q(32)
+#undef GPBT_Q
+      }
+      LAUNCH_CHECK();
+      return 0;
+    }
     const size_t smem = lowrank_smem_bytes(ch->Q);
     if (smem > (size_t)max_optin_smem()) return fail(GPBT_ESHAPE, "low-rank path: Q = %d too large", ch->Q);
     static size_t configured = 0;
@@ -526,7 +536,7 @@ extern "C" int gpbt_log_posterior(gpbt_chain_t ch, const double* X, double oob_v
       CU(cudaFuncSetAttribute(lowrank_loglike_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured = smem;
     }
-    lowrank_loglike_kernel<<<(unsigned)((N + kLrWarps - 1) / kLrWarps), kLrWarps * 32, smem, st>>>(prm);
+    lowrank_loglike_kernel<<<grid, kLrWarps * 32, smem, st>>>(prm);
     LAUNCH_CHECK();
     return 0;
   }

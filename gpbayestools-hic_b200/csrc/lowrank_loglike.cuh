@@ -135,4 +135,101 @@ __global__ void __launch_bounds__(kLrWarps * 32) lowrank_loglike_kernel(const Lo
     prm.lp[w] = -0.5 * (prm.s_perp + quad) - 0.5 * logdet2 - prm.logdetF_half + prm.sys_const;
 }
 
+// ---- register-resident variant, Q <= 32 ----------------------------------------------------------
+// Lane a owns row a of S in registers (QP = Q rounded up to a multiple of 4 is a compile-time
+// constant, so every index is static); pivots and L[c][b] travel by warp shuffle.  About 1.1k warp
+// instructions per walker at Q = 20 instead of the ~10k of the shared-memory kernel above, which
+// remains the fallback for Q > 32.  Rows/columns Q..QP-1 are identity padding (v = z = c0 = 0),
+// which leaves both the determinant and the quadratic form unchanged.
+template <int QP>
+__global__ void __launch_bounds__(kLrWarps * 32) lowrank_loglike_reg_kernel(const LowrankParams prm) {
+  constexpr int LD = QP + 2;                 // even stride (16-byte row alignment), conflict-light
+  __shared__ __align__(16) double Rr[QP * LD];            // R row-major, zero below the diagonal
+  __shared__ __align__(16) double zv[kLrWarps][2 * QP];   // per warp: z[QP], v[QP]
+  const int Q = prm.Q;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < QP * LD; i += blockDim.x) {
+    const int a = i / LD, k = i - a * LD;
+    double r = 0.0;
+    if (a < Q && k < Q && k >= a) r = prm.R[a * Q + k];
+    else if (a == k && a >= Q && a < QP) r = 1.0;
+    Rr[i] = r;
+  }
+  __syncthreads();
+  const int64_t w = (int64_t)blockIdx.x * kLrWarps + warp;
+  if (w >= prm.N) return;
+
+  bool ok = true;
+  for (int d = lane; d < prm.p; d += 32) {
+    const double x = prm.X[w * prm.p + d];
+    ok = ok && (x > prm.lo[d]) && (x < prm.hi[d]);
+  }
+  if (!__all_sync(0xffffffffu, ok)) {
+    if (lane == 0) prm.lp[w] = prm.oob_value;
+    return;
+  }
+  double* zs = zv[warp];
+  double* vs = zs + QP;
+  for (int a = lane; a < QP; a += 32) {
+    zs[a] = a < Q ? prm.z_mean[w * Q + a] : 0.0;
+    vs[a] = a < Q ? prm.z_var[w * Q + a] : 0.0;
+  }
+  __syncwarp();
+
+  const int a = lane < QP ? lane : QP - 1;   // idle lanes shadow the last row (results unused)
+  double rd[QP];                             // R[a][k] * v_k
+  double cv = (lane < Q) ? prm.c0[a] : 0.0;
+#pragma unroll
+  for (int k = 0; k < QP; k += 2) {
+    const double2 r = *reinterpret_cast<const double2*>(&Rr[a * LD + k]);
+    const double2 z = *reinterpret_cast<const double2*>(&zs[k]);
+    const double2 v = *reinterpret_cast<const double2*>(&vs[k]);
+    cv = fma(r.x, z.x, cv);
+    cv = fma(r.y, z.y, cv);
+    rd[k] = r.x * v.x;
+    rd[k + 1] = r.y * v.y;
+  }
+  double S[QP];                              // row a of S = I + R diag(v) R^T (entries b <= a are used)
+#pragma unroll
+  for (int b = 0; b < QP; b++) {
+    double s0 = (a == b) ? 1.0 : 0.0, s1 = 0.0;
+#pragma unroll
+    for (int k = b & ~1; k < QP; k += 2) {   // R[b][k] = 0 for k < b, so starting at the even k below b is exact
+      const double2 r = *reinterpret_cast<const double2*>(&Rr[b * LD + k]);
+      s0 = fma(rd[k], r.x, s0);
+      s1 = fma(rd[k + 1], r.y, s1);
+    }
+    S[b] = s0 + s1;
+  }
+
+  bool pd = true;
+  double quad = 0.0, pivot = 1.0;
+#pragma unroll
+  for (int b = 0; b < QP; b++) {
+    const double d = __shfl_sync(0xffffffffu, S[b], b);
+    pd = pd && (d > 0.0);
+    const double inv = rsqrt(d);
+    if (lane == b) pivot = d;
+    const double lab = S[b] * inv;                                   // L[a][b] (meaningful for a > b)
+    const double tb = __shfl_sync(0xffffffffu, cv, b) * inv;          // t_b = c_b / l_bb
+    quad = fma(tb, tb, quad);
+    cv = fma(-lab, tb, cv);
+#pragma unroll
+    for (int c = b + 1; c < QP; c++) {
+      const double lcb = __shfl_sync(0xffffffffu, lab, c);
+      S[c] = fma(-lab, lcb, S[c]);
+    }
+  }
+  double logdet2 = (lane < QP) ? log(pivot) : 0.0;                    // sum log d_b = 2 sum log l_bb
+  logdet2 = warp_sum(logdet2);
+  if (lane == 0) {
+    if (!pd) {
+      prm.lp[w] = prm.oob_value;
+      if (prm.n_notpd) atomicAdd(prm.n_notpd, 1);
+    } else {
+      prm.lp[w] = -0.5 * (prm.s_perp + quad) - 0.5 * logdet2 - prm.logdetF_half + prm.sys_const;
+    }
+  }
+}
+
 }  // namespace gpbt

@@ -173,6 +173,12 @@ def test_invariances():
             assert np.max(np.abs(ch.log_target(X[:700], -np.inf) - lp[:700])) <= 1e-10, tile
     finally:
         os.environ.pop("GPBT_PC_TILE", None)
+    # the shared-memory low-rank kernel (fallback for Q > 32) agrees with the register one
+    try:
+        os.environ["GPBT_LOWRANK_GENERIC"] = "1"
+        assert np.max(np.abs(ch.log_target(X[:700], -np.inf) - lp[:700])) <= 1e-10
+    finally:
+        os.environ.pop("GPBT_LOWRANK_GENERIC", None)
 
 
 def test_exp_accuracy():
