@@ -78,84 +78,110 @@ __global__ void __launch_bounds__(128) backtransform_mean_kernel(const Backtrans
 }
 
 // ---- dense covariance (PCA mode) on the FP64 tensor pipe --------------------------------------
-// grid = (row tiles of 32, N).  CTA = 4 warps; warp w handles column tiles w, w+4, ... of 32
-// columns.  D[i][j] = sum_k (v_k A[k][i]) * A[k][j]: A-operand fragment (row i = g, k = t) and
-// B-operand fragment (k = t, col j = g) both come from the same [q_pad][m_ld] array in shared
-// memory; m_ld = 4 mod 8 keeps those loads bank-conflict free.
+// Persistent CTAs (4 warps) keep A in shared memory and walk over (walker, 32-row tile) work items.
+// For an item, D[i][j] = Ctrunc[i][j] + sum_k (v_k A[k][i]) * A[k][j]: the accumulators are
+// initialised with the Ctrunc tile (its L2 latency overlaps the other warps' tensor work), the
+// A-operand fragment (row i = g, k = t) and the B-operand fragment (k = t, col j = g) both come from
+// the same [q_pad][m_ld] array (m_ld = 4 mod 8 keeps those loads bank-conflict free), and every
+// lane stores its two adjacent columns with one 16-byte store (64-byte row segments per quad).
+// The n8 column blocks of a row tile are dealt to the 4 warps as contiguous ranges.
 constexpr int kBtThreads = 128;
+constexpr int kBtWarps = kBtThreads / 32;
 constexpr int kBtRows = 32;
 
 inline size_t backtransform_smem_bytes(int q_pad, int m_ld) {
-  return sizeof(double) * ((size_t)q_pad * m_ld + (size_t)q_pad * kBtRows + q_pad);
+  return sizeof(double) * ((size_t)q_pad * m_ld + 2 * (size_t)q_pad * kBtRows);
 }
 
-__global__ void __launch_bounds__(kBtThreads) backtransform_cov_kernel(const BacktransformParams prm, int q_pad) {
+__global__ void __launch_bounds__(kBtThreads, 4) backtransform_cov_kernel(const BacktransformParams prm, int q_pad) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int m = prm.m, m_ld = prm.m_ld;
   double* As = reinterpret_cast<double*>(smem_raw);  // [q_pad][m_ld]
-  double* Av = As + (size_t)q_pad * m_ld;            // [q_pad][32]: v_k * A[k][i0 + r]
-  double* vs = Av + (size_t)q_pad * kBtRows;         // [q_pad]
+  double* Av = As + (size_t)q_pad * m_ld;            // [2][q_pad][32]: v_k * A[k][i0 + r], double buffered
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const int64_t w = blockIdx.y;
-  const int i0 = blockIdx.x * kBtRows;
 
-  for (int k = tid; k < q_pad; k += kBtThreads) vs[k] = k < prm.q ? prm.z_var[w * prm.ldz + k] : 0.0;
   for (int idx = tid; idx < q_pad * m_ld; idx += kBtThreads) {
     const int k = idx / m_ld;
     As[idx] = k < prm.q ? prm.A[idx] : 0.0;
   }
   __syncthreads();
-  for (int idx = tid; idx < q_pad * kBtRows; idx += kBtThreads) {
-    const int k = idx / kBtRows, r = idx - k * kBtRows;
-    Av[idx] = (i0 + r < m) ? vs[k] * As[(size_t)k * m_ld + i0 + r] : 0.0;
-  }
-  __syncthreads();
 
+  const int n_rt = (m + kBtRows - 1) / kBtRows;
+  const int64_t n_items = prm.N * n_rt;
   const int64_t ldc = prm.ld_cov, off = prm.col_off;
-  double* out = prm.cov + ((size_t)w * ldc + off + i0) * ldc;
-  const int n_ct = (m + 31) / 32;
-  for (int ct = warp; ct < n_ct; ct += kBtThreads / 32) {
-    const int j0 = ct * 32;
-    double acc[4][4][2];
+  const bool vec_ok = (ldc % 2 == 0) && (off % 2 == 0) && ((reinterpret_cast<uintptr_t>(prm.cov) & 15) == 0);
+  // contiguous range of n8 column blocks for this warp
+  const int n_nb = (m + 7) / 8;
+  const int nb_per = (n_nb + kBtWarps - 1) / kBtWarps;
+  const int nb_lo = min(warp * nb_per, n_nb), nb_hi = min(nb_lo + nb_per, n_nb);
+
+  int buf = 0;
+  for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, buf ^= 1) {
+    const int64_t w = item / n_rt;
+    const int i0 = (int)(item - w * n_rt) * kBtRows;
+    double* av = Av + (size_t)buf * q_pad * kBtRows;
+    for (int idx = tid; idx < q_pad * kBtRows; idx += kBtThreads) {
+      const int k = idx / kBtRows, r = idx - k * kBtRows;
+      const double v = k < prm.q ? prm.z_var[w * prm.ldz + k] : 0.0;
+      av[idx] = (i0 + r < m) ? v * As[(size_t)k * m_ld + i0 + r] : 0.0;
+    }
+    __syncthreads();  // (double buffered: the previous item's readers of the other buffer are done)
+    double* out = prm.cov + ((size_t)w * ldc + off + i0) * ldc + off;
+    for (int nb0 = nb_lo; nb0 < nb_hi; nb0 += 4) {
+      double acc[4][4][2];
+      // accumulators start from the Ctrunc tile; lane owns D[8mb + g][8nb + 2t + {0,1}]
 #pragma unroll
-    for (int mb = 0; mb < 4; mb++)
+      for (int mb = 0; mb < 4; mb++) {
+        const int i = i0 + 8 * mb + g;
 #pragma unroll
-      for (int nb = 0; nb < 4; nb++) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
-    for (int k0 = 0; k0 < q_pad; k0 += 4) {
-      double a[4], b[4];
+        for (int nb = 0; nb < 4; nb++) {
+          const int j = 8 * (nb0 + nb) + 2 * t;
+          const bool in = (i < m) && (nb0 + nb < nb_hi);
+          acc[mb][nb][0] = (in && j < m) ? __ldg(prm.Ctrunc + (size_t)i * m + j) : 0.0;
+          acc[mb][nb][1] = (in && j + 1 < m) ? __ldg(prm.Ctrunc + (size_t)i * m + j + 1) : 0.0;
+        }
+      }
+      for (int k0 = 0; k0 < q_pad; k0 += 4) {
+        double a[4], b[4];
 #pragma unroll
-      for (int mb = 0; mb < 4; mb++) a[mb] = Av[(k0 + t) * kBtRows + 8 * mb + g];
+        for (int mb = 0; mb < 4; mb++) a[mb] = av[(k0 + t) * kBtRows + 8 * mb + g];
 #pragma unroll
-      for (int nb = 0; nb < 4; nb++) {
-        const int j = j0 + 8 * nb + g;
-        b[nb] = j < m_ld ? As[(size_t)(k0 + t) * m_ld + j] : 0.0;
+        for (int nb = 0; nb < 4; nb++) {
+          const int j = 8 * (nb0 + nb) + g;
+          b[nb] = j < m_ld ? As[(size_t)(k0 + t) * m_ld + j] : 0.0;
+        }
+#pragma unroll
+        for (int nb = 0; nb < 4; nb++)
+          if (nb0 + nb < nb_hi) {
+#pragma unroll
+            for (int mb = 0; mb < 4; mb++) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
+          }
       }
 #pragma unroll
-      for (int mb = 0; mb < 4; mb++)
+      for (int mb = 0; mb < 4; mb++) {
+        if (i0 + 8 * mb + g >= m) continue;
+        double* row = out + (size_t)(8 * mb + g) * ldc;
 #pragma unroll
-        for (int nb = 0; nb < 4; nb++) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
-    }
-    // epilogue: + Ctrunc, store.  lane owns D[8mb + g][8nb + 2t + {0,1}]
-#pragma unroll
-    for (int mb = 0; mb < 4; mb++) {
-      const int i = i0 + 8 * mb + g;
-      if (i >= m) continue;
-#pragma unroll
-      for (int nb = 0; nb < 4; nb++) {
-        const int j = j0 + 8 * nb + 2 * t;
-#pragma unroll
-        for (int h = 0; h < 2; h++)
-          if (j + h < m)
-            out[(size_t)(8 * mb + g) * ldc + off + j + h] = acc[mb][nb][h] + prm.Ctrunc[(size_t)i * m + j + h];
+        for (int nb = 0; nb < 4; nb++) {
+          const int j = 8 * (nb0 + nb) + 2 * t;
+          if (nb0 + nb >= nb_hi || j >= m) continue;
+          if (vec_ok && j + 1 < m) {
+            *reinterpret_cast<double2*>(row + j) = make_double2(acc[mb][nb][0], acc[mb][nb][1]);
+          } else {
+            row[j] = acc[mb][nb][0];
+            if (j + 1 < m) row[j + 1] = acc[mb][nb][1];
+          }
+        }
       }
     }
-  }
-  // zero the parts of these rows that lie outside the diagonal block (multi-emulator chains)
-  if (ldc > m) {
-    for (int r = warp; r < kBtRows && i0 + r < m; r += kBtThreads / 32)
-      for (int64_t cidx = lane; cidx < ldc; cidx += 32)
-        if (cidx < off || cidx >= off + m) out[(size_t)r * ldc + cidx] = 0.0;
+    // zero the parts of these rows that lie outside the diagonal block (multi-emulator chains)
+    if (ldc > m) {
+      double* rows0 = prm.cov + ((size_t)w * ldc + off + i0) * ldc;
+      for (int r = warp; r < kBtRows && i0 + r < m; r += kBtWarps)
+        for (int64_t cidx = lane; cidx < ldc; cidx += 32)
+          if (cidx < off || cidx >= off + m) rows0[(size_t)r * ldc + cidx] = 0.0;
+    }
   }
 }
 

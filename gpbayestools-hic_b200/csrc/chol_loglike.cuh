@@ -6,15 +6,18 @@
 //     lp = -1/2 y.alpha - sum(log(diag(U)))
 // evaluated as  t = L^-1 y,  lp = -1/2 |t|^2 - sum(log(diag(L)))  with L = U^T.
 //
-// One CTA (4 warps) per walker, left-looking blocked factorisation with panel width 16.  The
+// One CTA (8 warps) per walker, left-looking blocked factorisation with panel width 16.  The
 // factor is written in place over the lower triangle of cov (HBM/L2 resident: a 300x300 FP64
 // matrix is 720 KB, more than one SM's shared memory); only the current (m-J) x 16 panel lives in
-// shared memory.  The panel update  P -= L[J:, :J] L[J:J+16, :J]^T  is the m^3/3 term and runs on
-// the FP64 tensor pipe (DMMA.8x8x4) with fragments loaded straight from global memory -- rows of
-// L are private to one warp, and the 16 rows of the B operand are re-read through L1.  The 16x16
-// diagonal block is factorised by one warp; the panel's triangular solve is one thread per row.
-// Several CTAs are resident per SM so one walker's sequential diagonal step overlaps another's
-// tensor work.
+// shared memory.
+//   update   P -= L[J:, :J] L[J:J+16, :J]^T  -- the m^3/3 term -- on the FP64 tensor pipe
+//            (DMMA.8x8x4); fragments come straight from global/L2 into ping-pong registers one
+//            8-column chunk ahead (rows of L are private to one warp; the 16 B-operand rows are
+//            shared through L1)
+//   diagonal 16x16 block: Cholesky in registers by one warp (lane = row, pivots and multipliers
+//            by shuffle), then its explicit inverse (lane = column)
+//   solve    P[16:, :] <- P[16:, :] Dinv^T as a DMMA product; t[J:J+16] = Dinv (y - L t) rides along
+// Two CTAs are resident per SM so one walker's sequential steps overlap the other's tensor work.
 #pragma once
 #include "common.cuh"
 
@@ -33,70 +36,77 @@ struct CholParams {
   int m;
 };
 
-constexpr int kChThreads = 128;
+constexpr int kChThreads = 256;
 constexpr int kChWarps = kChThreads / 32;
-constexpr int kChNB = 16;        // panel width
-constexpr int kChLd = kChNB + 1; // panel row stride in shared memory
-constexpr int kChMBW = 4;        // m8 row blocks per warp per update pass
+constexpr int kChNB = 16;   // panel width
+constexpr int kChLd = 20;   // panel / diagonal-block row stride in shared memory (conflict-free DMMA fragment loads)
+constexpr int kChMBW = 5;   // m8 row blocks per warp per update pass (one pass covers m <= 320)
 
 __host__ __device__ inline int chol_rows_pad(int m) {
   const int r = (int)round_up(m, 8);
   return r < kChNB ? kChNB : r;
 }
 inline size_t chol_smem_bytes(int m) {
-  const int rows = chol_rows_pad(m);
-  return sizeof(double) * ((size_t)rows * kChLd + (size_t)m + kChNB * kChLd + 64);
+  return sizeof(double) * ((size_t)chol_rows_pad(m) * kChLd + (size_t)m + 2 * kChNB * kChLd + 2 * kChNB + 8);
 }
 
-// four consecutive doubles of a row of L; 16-byte loads when the row stride keeps them aligned
-__device__ __forceinline__ void load4(const double* p, bool aligned, double (&v)[4]) {
-  if (aligned) {
-    const double2 a = *reinterpret_cast<const double2*>(p);
-    const double2 b = *reinterpret_cast<const double2*>(p + 2);
-    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
-  } else {
-    v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; v[3] = p[3];
-  }
+// two consecutive doubles of a row of L (16-byte load when the row stride keeps it aligned)
+__device__ __forceinline__ double2 load2(const double* p, bool aligned) {
+  if (aligned) return *reinterpret_cast<const double2*>(p);
+  return make_double2(p[0], p[1]);
 }
 
-// One pass of the panel update: this warp's row blocks  blk = warp + 4*(MBW*pass + i), i < MBW.
+// One pass of the panel update for this warp's row blocks blk = warp + 8*(MBW*pass + i), i < MBW.
+// k runs in chunks of 8: logical k slot t of step s is the actual column k0 + 2t + s (the same
+// permutation for the A and B operands); chunks alternate between two register buffers.
 template <int MBW>
 __device__ __forceinline__ void panel_update(const double* Lw, int m, int J, int nrows, int nb, bool aligned,
                                              double* P, int warp, int lane, int pass) {
   const int g = lane >> 2, t = lane & 3;
-  double acc[MBW][2][2];
-#pragma unroll
-  for (int i = 0; i < MBW; i++)
-#pragma unroll
-    for (int h = 0; h < 2; h++) acc[i][h][0] = acc[i][h][1] = 0.0;
   const int nblk = (nrows + 7) >> 3;
-  int blk[MBW], rowi[MBW];
+  double acc[MBW][2][2];
+  const double* arow[MBW];
+  bool act[MBW];
 #pragma unroll
   for (int i = 0; i < MBW; i++) {
-    blk[i] = warp + kChWarps * (MBW * pass + i);
-    rowi[i] = min(J + 8 * blk[i] + g, m - 1);  // clamped: padded rows are computed but never stored
+    acc[i][0][0] = acc[i][0][1] = acc[i][1][0] = acc[i][1][1] = 0.0;
+    const int blk = warp + kChWarps * (MBW * pass + i);
+    act[i] = blk < nblk;
+    // clamped: rows of the padded tail are computed but never stored
+    arow[i] = Lw + (size_t)min(J + 8 * blk + g, m - 1) * m + 2 * t;
   }
-  const int brow0 = min(J + g, m - 1), brow1 = min(J + 8 + g, m - 1);
-  for (int k0 = 0; k0 < J; k0 += 16) {
-    double b[2][4], a[MBW][4];
-    load4(Lw + (size_t)brow0 * m + k0 + 4 * t, aligned, b[0]);
-    load4(Lw + (size_t)brow1 * m + k0 + 4 * t, aligned, b[1]);
+  const double* brow0 = Lw + (size_t)min(J + g, m - 1) * m + 2 * t;
+  const double* brow1 = Lw + (size_t)min(J + 8 + g, m - 1) * m + 2 * t;
+  double2 a0[MBW], a1[MBW], b0[2], b1[2];
+  auto fetch = [&](double2 (&a)[MBW], double2 (&b)[2], int k0) {
+    b[0] = load2(brow0 + k0, aligned);
+    b[1] = load2(brow1 + k0, aligned);
 #pragma unroll
     for (int i = 0; i < MBW; i++)
-      if (blk[i] < nblk) load4(Lw + (size_t)rowi[i] * m + k0 + 4 * t, aligned, a[i]);
+      if (act[i]) a[i] = load2(arow[i] + k0, aligned);
+  };
+  auto mma = [&](const double2 (&a)[MBW], const double2 (&b)[2]) {
 #pragma unroll
-    for (int s = 0; s < 4; s++)
-#pragma unroll
-      for (int i = 0; i < MBW; i++)
-        if (blk[i] < nblk) {
-          dmma884(acc[i][0][0], acc[i][0][1], a[i][s], b[0][s]);
-          dmma884(acc[i][1][0], acc[i][1][1], a[i][s], b[1][s]);
-        }
+    for (int i = 0; i < MBW; i++)
+      if (act[i]) {
+        dmma884(acc[i][0][0], acc[i][0][1], a[i].x, b[0].x);
+        dmma884(acc[i][1][0], acc[i][1][1], a[i].x, b[1].x);
+        dmma884(acc[i][0][0], acc[i][0][1], a[i].y, b[0].y);
+        dmma884(acc[i][1][0], acc[i][1][1], a[i].y, b[1].y);
+      }
+  };
+  fetch(a0, b0, 0);
+#pragma unroll 1
+  for (int k0 = 0; k0 < J; k0 += 16) {  // J is a multiple of 16: two chunks per trip
+    fetch(a1, b1, k0 + 8);
+    mma(a0, b0);
+    if (k0 + 16 < J) fetch(a0, b0, k0 + 16);
+    mma(a1, b1);
   }
 #pragma unroll
   for (int i = 0; i < MBW; i++) {
-    const int r = 8 * blk[i] + g;
-    if (blk[i] < nblk && r < nrows) {
+    const int r = 8 * (warp + kChWarps * (MBW * pass + i)) + g;
+    if (act[i] && r < nrows) {
 #pragma unroll
       for (int h = 0; h < 2; h++) {
         const int c = 8 * h + 2 * t;
@@ -107,111 +117,142 @@ __device__ __forceinline__ void panel_update(const double* Lw, int m, int J, int
   }
 }
 
-__global__ void __launch_bounds__(kChThreads) chol_loglike_kernel(const CholParams prm) {
+__global__ void __launch_bounds__(kChThreads, 2) chol_loglike_kernel(const CholParams prm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int m = prm.m;
   const int rows_pad = chol_rows_pad(m);
-  double* P = reinterpret_cast<double*>(smem_raw);  // [rows_pad][17] current panel (rows J..m-1)
+  double* P = reinterpret_cast<double*>(smem_raw);  // [rows_pad][20] current panel (rows J..m-1)
   double* tv = P + (size_t)rows_pad * kChLd;        // [m] forward-solve vector t
-  double* D = tv + m;                               // [16][17] factorised diagonal block
-  double* red = D + kChNB * kChLd;                  // scratch
-  __shared__ int s_bad;
+  double* D = tv + m;                               // [16][20] Cholesky factor of the diagonal block
+  double* Dinv = D + kChNB * kChLd;                 // [16][20] its inverse (lower triangular)
+  double* red = Dinv + kChNB * kChLd;               // [16] right-hand side of the t solve
+  double* dinv = red + kChNB;                       // [16] 1 / diag(D)
+  int* s_bad = reinterpret_cast<int*>(dinv + kChNB);
 
   const int64_t w = blockIdx.x;
   if (prm.skip != nullptr && prm.skip[w]) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
   double* Lw = prm.cov + (size_t)w * m * m;
   const bool aligned = (m % 2 == 0) && ((reinterpret_cast<uintptr_t>(Lw) & 15) == 0);
-  if (tid == 0) s_bad = 0;
+  if (tid == 0) *s_bad = 0;
 
-  double logdet = 0.0;  // meaningful in warp 0
+  double logpiv = 0.0;  // warp 0, lane b: sum of log(pivot) over the panels' columns b
   for (int J = 0; J < m; J += kChNB) {
-    const int nrows = m - J;                 // panel rows J .. m-1
-    const int nb = min(kChNB, nrows);        // real columns in this panel
-    // 1. load the panel (+ cov_add); padded columns become identity columns
+    const int nrows = m - J;           // panel rows J .. m-1
+    const int nb = min(kChNB, nrows);  // real columns in this panel
+    const int nblk = (nrows + 7) >> 3;
+    // 1. load the panel (+ cov_add); a narrow last panel is padded with identity columns
+#pragma unroll 4
     for (int idx = tid; idx < rows_pad * kChNB; idx += kChThreads) {
       const int r = idx / kChNB, c = idx - r * kChNB;
       double v = 0.0;
       if (r < nrows && c < nb) {
         v = Lw[(size_t)(J + r) * m + J + c];
-        if (prm.cov_add) v += prm.cov_add[(size_t)(J + r) * m + J + c];
+        if (prm.cov_add) v += __ldg(prm.cov_add + (size_t)(J + r) * m + J + c);
       } else if (r == c) {
-        v = 1.0;  // identity padding of a narrow last panel
+        v = 1.0;
       }
       P[r * kChLd + c] = v;
     }
     __syncthreads();
-    // 2. P -= L[J:, :J] L[J:J+16, :J]^T
+    // 2. P -= L[J:, :J] L[J:J+16, :J]^T ;  red[c] = y[J+c] - L[J+c, :J] . t[:J]
     if (J > 0) {
-      const int per_warp = ((nrows + 7) / 8 + kChWarps - 1) / kChWarps;
+      const int per_warp = (nblk + kChWarps - 1) / kChWarps;
       for (int pass = 0; pass * kChMBW < per_warp; pass++)
         panel_update<kChMBW>(Lw, m, J, nrows, nb, aligned, P, warp, lane, pass);
-      __syncthreads();
     }
-    // 3. factorise the 16x16 diagonal block (warp 0; lane = row) and forward-solve 16 entries of t
-    if (warp == 0) {
-      const int r = lane;
-      for (int c = 0; c < kChNB; c++) {
-        const double d = P[c * kChLd + c];
-        if (!(d > 0.0)) { if (lane == 0) s_bad = 1; break; }
-        const double l = sqrt(d), inv = 1.0 / l;
-        logdet += log(l);
-        __syncwarp();
-        if (r == c) P[c * kChLd + c] = l;
-        if (r > c && r < kChNB) P[r * kChLd + c] *= inv;
-        __syncwarp();
-        if (r > c && r < kChNB) {
-          const double lrc = P[r * kChLd + c];
-          for (int c2 = c + 1; c2 <= r; c2++) P[r * kChLd + c2] = fma(-lrc, P[c2 * kChLd + c], P[r * kChLd + c2]);
-        }
-        __syncwarp();
-      }
-      for (int idx = lane; idx < kChNB * kChNB; idx += 32) {
-        const int rr = idx / kChNB, cc = idx - rr * kChNB;
-        D[rr * kChLd + cc] = P[rr * kChLd + cc];
-      }
-    }
-    __syncthreads();
-    if (s_bad) break;
-    // 4. rows below the diagonal block: P[r, :] <- P[r, :] D^-T  (one thread per row)
-    for (int r = kChNB + tid; r < nrows; r += kChThreads) {
-      double x[kChNB];
-#pragma unroll
-      for (int c = 0; c < kChNB; c++) x[c] = P[r * kChLd + c];
-#pragma unroll
-      for (int c = 0; c < kChNB; c++) {
-        double s = x[c];
-#pragma unroll
-        for (int k = 0; k < c; k++) s = fma(-x[k], D[c * kChLd + k], s);
-        x[c] = s / D[c * kChLd + c];
-      }
-#pragma unroll
-      for (int c = 0; c < kChNB; c++) P[r * kChLd + c] = x[c];
-    }
-    // 5. t[J:J+nb]: rhs = y - L[J:J+nb, :J] t[:J]  (warp per row, lanes over k), then D^-1
     for (int c = warp; c < nb; c += kChWarps) {
-      double s = 0.0;
+      double sdot = 0.0;
       const double* Lrow = Lw + (size_t)(J + c) * m;
-      for (int k = lane; k < J; k += 32) s = fma(Lrow[k], tv[k], s);
-      s = warp_sum(s);
+      for (int k = lane; k < J; k += 32) sdot = fma(Lrow[k], tv[k], sdot);
+      sdot = warp_sum(sdot);
       if (lane == 0) {
         double y = prm.mean[w * m + J + c];
         if (prm.y_exp) y -= prm.y_exp[J + c];
-        red[c] = y - s;
+        red[c] = y - sdot;
       }
     }
     __syncthreads();
+    // 3. diagonal block (warp 0): Cholesky in registers, lane = row; then the inverse, lane = column
     if (warp == 0) {
-      // sequential 16-step forward substitution, lane = row
-      double rhs = lane < nb ? red[lane] : 0.0;
-      for (int c = 0; c < nb; c++) {
-        const double tc = __shfl_sync(0xffffffffu, rhs, c) / D[c * kChLd + c];
-        if (lane == c) rhs = tc;
-        else if (lane > c && lane < nb) rhs = fma(-D[lane * kChLd + c], tc, rhs);
+      const int r = lane & 15;
+      double S[kChNB];
+#pragma unroll
+      for (int c = 0; c < kChNB; c++) S[c] = P[r * kChLd + c];
+      bool pd = true;
+#pragma unroll
+      for (int b = 0; b < kChNB; b++) {
+        const double d = __shfl_sync(0xffffffffu, S[b], b);
+        pd = pd && (d > 0.0);
+        const double inv = rsqrt(d);
+        if (lane == b) { logpiv += log(d); dinv[b] = inv; }
+        const double lab = (r == b) ? d * inv : S[b] * inv;  // L[r][b]; the diagonal is sqrt(d)
+        S[b] = lab;
+#pragma unroll
+        for (int c = b + 1; c < kChNB; c++) {
+          const double lcb = __shfl_sync(0xffffffffu, lab, c);
+          S[c] = fma(-lab, lcb, S[c]);
+        }
       }
-      if (lane < nb) tv[J + lane] = rhs;
+      if (!pd && lane == 0) *s_bad = 1;
+      if (lane < kChNB) {
+#pragma unroll
+        for (int c = 0; c < kChNB; c++) D[r * kChLd + c] = (c <= r) ? S[c] : 0.0;
+      }
+      __syncwarp();
+      // X = D^-1 by forward substitution, lane j owns column j: X[i][j] = (delta_ij - sum_k D[i][k] X[k][j]) / D[i][i]
+      {
+        const int j = lane & 15;
+        double X[kChNB];
+#pragma unroll
+        for (int i = 0; i < kChNB; i++) {
+          double sx = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+          for (int k = 0; k < i; k++) sx = fma(-D[i * kChLd + k], X[k], sx);
+          X[i] = (i >= j) ? sx * dinv[i] : 0.0;
+        }
+        if (lane < kChNB) {
+#pragma unroll
+          for (int i = 0; i < kChNB; i++) Dinv[i * kChLd + j] = X[i];
+        }
+      }
     }
-    // 6. write the panel back (lower part only matters; rows J.., real columns)
+    __syncthreads();
+    if (*s_bad) break;
+    // 4. rows below the diagonal block: P[r, :] <- P[r, :] Dinv^T  (DMMA; blocks 2.. dealt to warps)
+    for (int blk = 2 + warp; blk < nblk; blk += kChWarps) {
+      double a[4], acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+      double* prow = P + (size_t)(8 * blk + g) * kChLd;
+#pragma unroll
+      for (int s = 0; s < 4; s++) a[s] = prow[4 * s + t];
+      __syncwarp();  // every lane has read its row fragment before anyone overwrites the rows
+#pragma unroll
+      for (int s = 0; s < 4; s++) {
+        dmma884(acc[0][0], acc[0][1], a[s], Dinv[(size_t)g * kChLd + 4 * s + t]);
+        dmma884(acc[1][0], acc[1][1], a[s], Dinv[(size_t)(8 + g) * kChLd + 4 * s + t]);
+      }
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        prow[8 * h + 2 * t] = acc[h][0];
+        prow[8 * h + 2 * t + 1] = acc[h][1];
+      }
+    }
+    //    the factor of the diagonal block replaces P's first 16 rows; t[J:J+16] = Dinv * red
+    if (warp == kChWarps - 1) {
+      for (int idx = lane; idx < kChNB * kChNB; idx += 32) {
+        const int rr = idx / kChNB, cc = idx - rr * kChNB;
+        P[rr * kChLd + cc] = D[rr * kChLd + cc];
+      }
+      if (lane < nb) {
+        double sx = 0.0;
+        for (int k = 0; k <= lane; k++) sx = fma(Dinv[lane * kChLd + k], red[k], sx);
+        tv[J + lane] = sx;
+      }
+    }
+    __syncthreads();
+    // 5. write the panel back (rows J.., real columns)
+#pragma unroll 4
     for (int idx = tid; idx < nrows * kChNB; idx += kChThreads) {
       const int r = idx / kChNB, c = idx - r * kChNB;
       if (c < nb) Lw[(size_t)(J + r) * m + J + c] = P[r * kChLd + c];
@@ -220,14 +261,16 @@ __global__ void __launch_bounds__(kChThreads) chol_loglike_kernel(const CholPara
   }
   if (warp == 0) {
     double out;
-    if (s_bad) {
+    const int bad = *s_bad;
+    double q2 = 0.0;
+    for (int k = lane; k < m; k += 32) q2 = fma(tv[k], tv[k], q2);
+    q2 = warp_sum(q2);
+    const double ld2 = warp_sum(logpiv);  // sum log d = 2 sum log l
+    if (bad) {
       out = prm.notpd_value;
       if (lane == 0 && prm.n_notpd) atomicAdd(prm.n_notpd, 1);
     } else {
-      double q2 = 0.0;
-      for (int k = lane; k < m; k += 32) q2 = fma(tv[k], tv[k], q2);
-      q2 = warp_sum(q2);
-      out = -0.5 * q2 - logdet + prm.add_const;
+      out = -0.5 * q2 - 0.5 * ld2 + prm.add_const;
     }
     if (lane == 0) prm.lp[w] = out;
   }

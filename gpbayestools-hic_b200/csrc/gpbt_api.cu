@@ -261,8 +261,10 @@ int run_backtransform(gpbt_emulator_t e, const double* zm, const double* zv, int
       CU(cudaFuncSetAttribute(backtransform_cov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured = smem;
     }
-    dim3 grid((unsigned)((e->m + kBtRows - 1) / kBtRows), (unsigned)N);
-    if (N > 65535) return fail(GPBT_ESHAPE, "backtransform: chunk the walkers (N = %lld > 65535)", (long long)N);
+    const int64_t items = N * ((e->m + kBtRows - 1) / kBtRows);
+    int per_sm = (int)std::min<size_t>(4, (228 * 1024 - 4096) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    const unsigned grid = (unsigned)std::min<int64_t>(items, (int64_t)148 * per_sm);
     backtransform_cov_kernel<<<grid, kBtThreads, smem, st>>>(prm, e->q_pad);
     LAUNCH_CHECK();
   }

@@ -27,7 +27,10 @@ def _stream_ptr(torch):
 
 def as_rows(X, p=None):
     """float64 C-contiguous [N, p]; a 1-D input is one row (np.array(X, ndmin=2) in the reference)."""
-    X = np.ascontiguousarray(np.array(X, dtype=np.float64, ndmin=2))
+    X = np.asarray(X, dtype=np.float64)   # no copy for float64 input
+    if X.ndim < 2:
+        X = X.reshape(1, -1)
+    X = np.ascontiguousarray(X)
     if p is not None and X.shape[1] != p:
         raise ValueError("expected %d parameters per row, got %d" % (p, X.shape[1]))
     return X
