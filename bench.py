@@ -386,7 +386,8 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         if args.cpu_rows is None:
-            args.cpu_rows = 2048
+            # bounded sample per step so that steps x rows stays near 3e5 evaluations (~1-2 min on 16 cores)
+            args.cpu_rows = int(min(4096, max(256, 3e5 // max(args.steps, 1))))
         run_reference(args)
     else:
         if args.cpu_rows is None:

@@ -15,7 +15,7 @@ PATH_AUTO, PATH_DENSE, PATH_LOWRANK = 0, 1, 2
 # every symbol include/gpbt.h declares (tests/test_cabi.py checks the library exports them all)
 SYMBOLS = [
     "gpbt_last_error", "gpbt_version", "gpbt_emulator_create", "gpbt_emulator_destroy",
-    "gpbt_pc_predict", "gpbt_backtransform", "gpbt_mvn_loglike", "gpbt_chain_create",
+    "gpbt_pc_predict", "gpbt_backtransform", "gpbt_backtransform_diag", "gpbt_mvn_loglike", "gpbt_chain_create",
     "gpbt_chain_destroy", "gpbt_chain_predict", "gpbt_log_posterior", "gpbt_log_posterior_host",
     "gpbt_chain_workspace_bytes", "gpbt_launch_count", "gpbt_debug_exp_neg",
 ]
@@ -39,6 +39,7 @@ def _load():
     lib.gpbt_emulator_destroy.argtypes = [vp]
     lib.gpbt_pc_predict.argtypes = [vp, dp, dp, dp, dp, i64, i64, vp]
     lib.gpbt_backtransform.argtypes = [vp, dp, dp, i64, dp, i64, dp, i64, i64, i64, vp]
+    lib.gpbt_backtransform_diag.argtypes = [vp, dp, dp, i64, dp, dp, i64, i64, i64, vp]
     lib.gpbt_mvn_loglike.argtypes = [dp, dp, dp, dp, dp, dp, dbl, i64, i32, vp]
     lib.gpbt_chain_create.argtypes = [C.POINTER(vp), C.POINTER(vp), i32, i32, dp, dp, dp, dp, dp, dp, dbl, dbl]
     lib.gpbt_chain_destroy.argtypes = [vp]

@@ -27,6 +27,7 @@ struct BacktransformParams {
   const double* __restrict__ Ctrunc;  // [m, m] (PCA mode)
   double* __restrict__ mean;          // [N, ld_mean]
   double* __restrict__ cov;           // [N, ld_cov, ld_cov] or null
+  double* __restrict__ var_diag;      // [N, ld_mean] or null: diag(cov) only (posterior-predictive sweeps)
   int64_t ldz, ld_mean, ld_cov, col_off, N;
   int q, m, m_ld, flags;
 };
@@ -54,7 +55,7 @@ __global__ void __launch_bounds__(128) backtransform_mean_kernel(const Backtrans
       double s = 0.0;
       for (int k = 0; k < prm.q; k++) s = fma(zs[k], prm.A[(size_t)k * prm.m_ld + o], s);
       mean = s + prm.mu[o];
-      if (exp_diag) {
+      if (exp_diag || prm.var_diag != nullptr) {
         double d = prm.Ctrunc[(size_t)o * prm.m + o];
         for (int k = 0; k < prm.q; k++) {
           const double a = prm.A[(size_t)k * prm.m_ld + o];
@@ -69,6 +70,7 @@ __global__ void __launch_bounds__(128) backtransform_mean_kernel(const Backtrans
       var = f * f;
     }
     prm.mean[w * prm.ld_mean + prm.col_off + o] = mean;
+    if (prm.var_diag != nullptr) prm.var_diag[w * prm.ld_mean + prm.col_off + o] = var;
     if (diag_cov && prm.cov != nullptr) {
       // whole row (col_off + o) of this walker's matrix: zeros + the diagonal entry
       double* row = prm.cov + ((size_t)w * prm.ld_cov + prm.col_off + o) * prm.ld_cov;

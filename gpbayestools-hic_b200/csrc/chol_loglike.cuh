@@ -14,8 +14,9 @@
 //            (DMMA.8x8x4); fragments come straight from global/L2 into ping-pong registers one
 //            8-column chunk ahead (rows of L are private to one warp; the 16 B-operand rows are
 //            shared through L1)
-//   diagonal 16x16 block: Cholesky in registers by one warp (lane = row, pivots and multipliers
-//            by shuffle), then its explicit inverse (lane = column)
+//   diagonal 16x16 block: warp 0 alone updates it and factorises it in registers (lane = row, pivots
+//            and multipliers by shuffle; 16 identity rows ride along and end as the inverse) while
+//            the other 7 warps run the bulk of the update
 //   solve    P[16:, :] <- P[16:, :] Dinv^T as a DMMA product; t[J:J+16] = Dinv (y - L t) rides along
 // Two CTAs are resident per SM so one walker's sequential steps overlap the other's tensor work.
 #pragma once
@@ -56,12 +57,12 @@ __device__ __forceinline__ double2 load2(const double* p, bool aligned) {
   return make_double2(p[0], p[1]);
 }
 
-// One pass of the panel update for this warp's row blocks blk = warp + 8*(MBW*pass + i), i < MBW.
+// Panel update for the m8 row blocks  blk = first + stride * i,  i < MBW  (blocks >= nblk are idle).
 // k runs in chunks of 8: logical k slot t of step s is the actual column k0 + 2t + s (the same
 // permutation for the A and B operands); chunks alternate between two register buffers.
 template <int MBW>
 __device__ __forceinline__ void panel_update(const double* Lw, int m, int J, int nrows, int nb, bool aligned,
-                                             double* P, int warp, int lane, int pass) {
+                                             double* P, int first, int stride, int lane) {
   const int g = lane >> 2, t = lane & 3;
   const int nblk = (nrows + 7) >> 3;
   double acc[MBW][2][2];
@@ -70,7 +71,7 @@ __device__ __forceinline__ void panel_update(const double* Lw, int m, int J, int
 #pragma unroll
   for (int i = 0; i < MBW; i++) {
     acc[i][0][0] = acc[i][0][1] = acc[i][1][0] = acc[i][1][1] = 0.0;
-    const int blk = warp + kChWarps * (MBW * pass + i);
+    const int blk = first + stride * i;
     act[i] = blk < nblk;
     // clamped: rows of the padded tail are computed but never stored
     arow[i] = Lw + (size_t)min(J + 8 * blk + g, m - 1) * m + 2 * t;
@@ -105,7 +106,7 @@ __device__ __forceinline__ void panel_update(const double* Lw, int m, int J, int
   }
 #pragma unroll
   for (int i = 0; i < MBW; i++) {
-    const int r = 8 * (warp + kChWarps * (MBW * pass + i)) + g;
+    const int r = 8 * (first + stride * i) + g;
     if (act[i] && r < nrows) {
 #pragma unroll
       for (int h = 0; h < 2; h++) {
@@ -126,8 +127,7 @@ __global__ void __launch_bounds__(kChThreads, 2) chol_loglike_kernel(const CholP
   double* D = tv + m;                               // [16][20] Cholesky factor of the diagonal block
   double* Dinv = D + kChNB * kChLd;                 // [16][20] its inverse (lower triangular)
   double* red = Dinv + kChNB * kChLd;               // [16] right-hand side of the t solve
-  double* dinv = red + kChNB;                       // [16] 1 / diag(D)
-  int* s_bad = reinterpret_cast<int*>(dinv + kChNB);
+  int* s_bad = reinterpret_cast<int*>(red + kChNB);
 
   const int64_t w = blockIdx.x;
   if (prm.skip != nullptr && prm.skip[w]) return;
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(kChThreads, 2) chol_loglike_kernel(const CholP
     const int nb = min(kChNB, nrows);  // real columns in this panel
     const int nblk = (nrows + 7) >> 3;
     // 1. load the panel (+ cov_add); a narrow last panel is padded with identity columns
-#pragma unroll 4
+#pragma unroll 8
     for (int idx = tid; idx < rows_pad * kChNB; idx += kChThreads) {
       const int r = idx / kChNB, c = idx - r * kChNB;
       double v = 0.0;
@@ -156,38 +156,39 @@ __global__ void __launch_bounds__(kChThreads, 2) chol_loglike_kernel(const CholP
       P[r * kChLd + c] = v;
     }
     __syncthreads();
-    // 2. P -= L[J:, :J] L[J:J+16, :J]^T ;  red[c] = y[J+c] - L[J+c, :J] . t[:J]
-    if (J > 0) {
-      const int per_warp = (nblk + kChWarps - 1) / kChWarps;
-      for (int pass = 0; pass * kChMBW < per_warp; pass++)
-        panel_update<kChMBW>(Lw, m, J, nrows, nb, aligned, P, warp, lane, pass);
-    }
-    for (int c = warp; c < nb; c += kChWarps) {
-      double sdot = 0.0;
-      const double* Lrow = Lw + (size_t)(J + c) * m;
-      for (int k = lane; k < J; k += 32) sdot = fma(Lrow[k], tv[k], sdot);
-      sdot = warp_sum(sdot);
-      if (lane == 0) {
-        double y = prm.mean[w * m + J + c];
-        if (prm.y_exp) y -= prm.y_exp[J + c];
-        red[c] = y - sdot;
+    // pull the next panel (rows J+16.., columns J+16..J+31 of cov, still untouched input) towards L2
+    // while this one is being processed: its load is otherwise a chain of exposed HBM latencies
+    if (J + kChNB < m) {
+      for (int r = tid; r < nrows - kChNB; r += kChThreads) {
+        const double* nxt = Lw + (size_t)(J + kChNB + r) * m + J + kChNB;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + min(kChNB, nrows - kChNB) - 1));
       }
     }
-    __syncthreads();
-    // 3. diagonal block (warp 0): Cholesky in registers, lane = row; then the inverse, lane = column
+    // 2+3. Warp 0 walks the critical path: update of the two diagonal row blocks, then the 16x16
+    //      Cholesky.  Warps 1..7 meanwhile update the rows below and form the right-hand side of
+    //      the t solve,  red[c] = y[J+c] - L[J+c, :J] . t[:J].
     if (warp == 0) {
+      if (J > 0) {
+        panel_update<2>(Lw, m, J, nrows, nb, aligned, P, 0, 1, lane);
+        __syncwarp();
+      }
+      // lanes 0..15 own the rows of the diagonal block, lanes 16..31 the rows of an identity matrix:
+      // the same right-looking elimination that leaves L in the first group leaves L^-T in the
+      // second (row 16+j ends as column j of L^-1), so the inverse costs no extra code.
       const int r = lane & 15;
       double S[kChNB];
 #pragma unroll
-      for (int c = 0; c < kChNB; c++) S[c] = P[r * kChLd + c];
+      for (int c = 0; c < kChNB; c++) S[c] = (lane < 16) ? P[r * kChLd + c] : (r == c ? 1.0 : 0.0);
       bool pd = true;
+      double piv = 1.0;
 #pragma unroll
       for (int b = 0; b < kChNB; b++) {
         const double d = __shfl_sync(0xffffffffu, S[b], b);
         pd = pd && (d > 0.0);
         const double inv = rsqrt(d);
-        if (lane == b) { logpiv += log(d); dinv[b] = inv; }
-        const double lab = (r == b) ? d * inv : S[b] * inv;  // L[r][b]; the diagonal is sqrt(d)
+        if (lane == b) piv = d;
+        const double lab = (lane == b) ? d * inv : S[b] * inv;  // L[r][b]  |  (L^-T)[j][b];  diagonal = sqrt(d)
         S[b] = lab;
 #pragma unroll
         for (int c = b + 1; c < kChNB; c++) {
@@ -195,26 +196,31 @@ __global__ void __launch_bounds__(kChThreads, 2) chol_loglike_kernel(const CholP
           S[c] = fma(-lab, lcb, S[c]);
         }
       }
+      if (lane < 16) logpiv += log(piv);
       if (!pd && lane == 0) *s_bad = 1;
-      if (lane < kChNB) {
+      if (lane < 16) {
 #pragma unroll
         for (int c = 0; c < kChNB; c++) D[r * kChLd + c] = (c <= r) ? S[c] : 0.0;
+      } else {
+        // lane 16+j holds (L^-T)[j][c] = (L^-1)[c][j] for c >= j
+#pragma unroll
+        for (int c = 0; c < kChNB; c++) Dinv[c * kChLd + r] = (c >= r) ? S[c] : 0.0;
       }
-      __syncwarp();
-      // X = D^-1 by forward substitution, lane j owns column j: X[i][j] = (delta_ij - sum_k D[i][k] X[k][j]) / D[i][i]
-      {
-        const int j = lane & 15;
-        double X[kChNB];
-#pragma unroll
-        for (int i = 0; i < kChNB; i++) {
-          double sx = (i == j) ? 1.0 : 0.0;
-#pragma unroll
-          for (int k = 0; k < i; k++) sx = fma(-D[i * kChLd + k], X[k], sx);
-          X[i] = (i >= j) ? sx * dinv[i] : 0.0;
-        }
-        if (lane < kChNB) {
-#pragma unroll
-          for (int i = 0; i < kChNB; i++) Dinv[i * kChLd + j] = X[i];
+    } else {
+      if (J > 0) {
+        const int bulk = nblk - 2;  // row blocks 2 .. nblk-1 over 7 warps, kChMBW per pass
+        for (int base = 0; base < bulk; base += (kChWarps - 1) * kChMBW)
+          panel_update<kChMBW>(Lw, m, J, nrows, nb, aligned, P, 2 + base + (warp - 1), kChWarps - 1, lane);
+      }
+      for (int c = warp - 1; c < nb; c += kChWarps - 1) {
+        double sdot = 0.0;
+        const double* Lrow = Lw + (size_t)(J + c) * m;
+        for (int k = lane; k < J; k += 32) sdot = fma(Lrow[k], tv[k], sdot);
+        sdot = warp_sum(sdot);
+        if (lane == 0) {
+          double y = prm.mean[w * m + J + c];
+          if (prm.y_exp) y -= prm.y_exp[J + c];
+          red[c] = y - sdot;
         }
       }
     }

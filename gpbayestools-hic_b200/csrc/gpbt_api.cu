@@ -242,9 +242,10 @@ int run_pc_predict(gpbt_emulator_t e, const double* X, const double* extra, doub
 
 int run_backtransform(gpbt_emulator_t e, const double* zm, const double* zv, int64_t ldz, double* mean,
                       int64_t ld_mean, double* cov, int64_t ld_cov, int64_t col_off, int64_t N,
-                      cudaStream_t st) {
+                      cudaStream_t st, double* var_diag = nullptr) {
   if (N <= 0) return 0;
   BacktransformParams prm;
+  prm.var_diag = var_diag;
   prm.z_mean = zm; prm.z_var = zv; prm.A = e->A; prm.mu = e->mu; prm.scale = e->scale;
   prm.Ctrunc = e->Ctrunc; prm.mean = mean; prm.cov = cov; prm.ldz = ldz; prm.ld_mean = ld_mean;
   prm.ld_cov = ld_cov; prm.col_off = col_off; prm.N = N; prm.q = e->q; prm.m = e->m; prm.m_ld = e->m_ld;
@@ -353,6 +354,14 @@ extern "C" int gpbt_backtransform(gpbt_emulator_t emu, const double* zm, const d
     if (r) return r;
   }
   return 0;
+}
+
+extern "C" int gpbt_backtransform_diag(gpbt_emulator_t emu, const double* zm, const double* zv, int64_t ldz,
+                                       double* mean, double* var, int64_t ld, int64_t col_off, int64_t N,
+                                       void* stream) {
+  if (!emu || !zm || !zv || !mean || !var || N < 0 || ld < col_off + emu->m)
+    return fail(GPBT_EINVAL, "gpbt_backtransform_diag: bad argument");
+  return run_backtransform(emu, zm, zv, ldz, mean, ld, nullptr, 0, col_off, N, (cudaStream_t)stream, var);
 }
 
 extern "C" int gpbt_mvn_loglike(const double* mean, const double* y_exp, double* cov, const double* cov_add,

@@ -66,6 +66,38 @@ class DeviceEmulator:
             None if cov is None else cov.data_ptr(), st.m, 0, N, _stream_ptr(torch)))
         return (mean, cov) if return_cov else mean
 
+    def predict_diag_device(self, X_d, extra_d=None):
+        """mean [N, m] and diag(cov) [N, m] on the device (no N*m^2 covariance is formed)"""
+        torch = _torch()
+        st = self.state
+        N = X_d.shape[0]
+        zm, zv = self.pc_predict_device(X_d, extra_d)
+        mean = torch.empty((N, st.m), dtype=torch.float64, device=X_d.device)
+        var = torch.empty_like(mean)
+        _lib.check(_lib.lib.gpbt_backtransform_diag(
+            st.handle(), zm.data_ptr(), zv.data_ptr(), st.q, mean.data_ptr(), var.data_ptr(), st.m, 0, N,
+            _stream_ptr(torch)))
+        return mean, var
+
+    def predict_diag(self, X, extra_std=0, chunk=1 << 18):
+        """NumPy in/out: (mean, var) with var = diag of the covariance predict() would return."""
+        torch = _torch()
+        st = self.state
+        X = as_rows(X, st.p)
+        N = X.shape[0]
+        extra = np.asarray(extra_std, dtype=np.float64).reshape(-1)
+        if extra.size == 1:
+            extra = None if extra[0] == 0.0 else np.full(N, extra[0])
+        mean, var = np.empty((N, st.m)), np.empty((N, st.m))
+        for s in range(0, N, chunk):
+            e = min(N, s + chunk)
+            X_d = torch.from_numpy(X[s:e]).cuda()
+            extra_d = None if extra is None else torch.from_numpy(np.ascontiguousarray(extra[s:e])).cuda()
+            m_d, v_d = self.predict_diag_device(X_d, extra_d)
+            mean[s:e] = m_d.cpu().numpy()
+            var[s:e] = v_d.cpu().numpy()
+        return mean, var
+
     # -- numpy in, numpy out (the reference's signature) --------------------------------------
     def predict(self, X, return_cov=True, extra_std=0):
         torch = _torch()

@@ -176,6 +176,11 @@ class Emulator:
         value per sample) is added in quadrature to every GP's predictive standard deviation."""
         return self._dev().predict(X, return_cov=return_cov, extra_std=extra_std)
 
+    def predict_diag(self, X, extra_std=0):
+        """(mean, var): `var` is the diagonal of the covariance `predict` returns, without forming
+        the nsamples x nobs x nobs array -- for posterior-predictive and sensitivity sweeps."""
+        return self._dev().predict_diag(X, extra_std=extra_std)
+
     # ---- pickling: device handles never travel -------------------------------------------------
     def __getstate__(self):
         d = dict(self.__dict__)

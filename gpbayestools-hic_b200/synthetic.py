@@ -112,3 +112,33 @@ def systematic_cov(m, rank=5, scale=0.02, seed=5):
     rng = np.random.default_rng(seed)
     G = scale * rng.standard_normal((m, rank))
     return G @ G.T
+
+
+def untrained_state_arrays(p, n, m, q, kind="RBF", seed=17, ell_range=(0.8, 4.0), c=50.0, sn=0.01):
+    """A self-consistent emulator state of a given shape WITHOUT the L-BFGS hyper-parameter search
+    (which takes minutes at n = 1000): data from the synthetic simulator, StandardScaler + whitened
+    PCA as src/emulator.py:260-272 does, fixed plausible kernel hyper-parameters, and alpha_ / L_
+    exactly as sklearn's fit builds them from those (_gpr.py:349-367).  For throughput runs at
+    shapes that have no golden file; keyword arguments for EmulatorState.from_arrays."""
+    from scipy.linalg import cho_solve
+    from .state import cholesky_of_kernel
+    rng = np.random.default_rng(seed)
+    sim = Simulator(p, m)
+    Xtr = design(p, n)
+    Y = sim(Xtr) + 0.01 * rng.standard_normal((n, m))
+    mu, scale = Y.mean(0), Y.std(0)
+    Ys = (Y - mu) / scale
+    U, S, Vt = np.linalg.svd(Ys, full_matrices=False)
+    expl_var = S ** 2 / (n - 1)
+    Z = (U * S)[:, :q] / np.sqrt(expl_var[:q])                      # whitened PC scores
+    trans = Vt * np.sqrt(expl_var)[:, None] * scale                 # _trans_matrix (src/emulator.py:335-339)
+    A, B = trans[:q], trans[q:]
+    Ctrunc = B.T @ B
+    Ctrunc[np.diag_indices(m)] += 1e-4 * scale ** 2
+    span = box(p)[1] - box(p)[0]
+    ell = span * rng.uniform(ell_range[0], ell_range[1], (q, p))
+    cs, sns = np.full(q, c), np.full(q, sn)
+    L = np.stack([cholesky_of_kernel(kind, Xtr, cs[j], ell[j], sns[j]) for j in range(q)])
+    alpha = np.stack([cho_solve((L[j], True), Z[:, j]) for j in range(q)])
+    return dict(kind=kind, Xtr=Xtr, ell=ell, c=cs, sn=sns, alpha=alpha, mu=mu, scale=scale, A=A,
+                Ctrunc=Ctrunc, L=L)

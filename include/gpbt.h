@@ -83,6 +83,13 @@ int gpbt_backtransform(gpbt_emulator_t emu, const double* z_mean_dev, const doub
                        int64_t ldz, double* mean_dev, int64_t ld_mean, double* cov_dev,
                        int64_t ld_cov, int64_t col_off, int64_t N, void* stream);
 
+/* Mean and only the DIAGONAL of the observable-space covariance (var_dev[i*ld + col_off + o]); the
+ * form posterior-predictive / sensitivity sweeps need (examples/SensitivityAnalysis.ipynb cell 4,
+ * BASELINE config 5), where N * m^2 covariances could not be stored, let alone returned.        */
+int gpbt_backtransform_diag(gpbt_emulator_t emu, const double* z_mean_dev, const double* z_var_dev,
+                            int64_t ldz, double* mean_dev, double* var_dev, int64_t ld,
+                            int64_t col_off, int64_t N, void* stream);
+
 /* ---- kernel (c): batched Cholesky log-likelihood ------------------------------------------ *
  * Replaces list(map(mvn_loglike, dY, cov)) (src/mcmc.py:23-65, 293) including dY = mean - y_exp
  * and cov + expdata_cov (src/mcmc.py:288-290):

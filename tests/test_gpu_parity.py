@@ -54,6 +54,8 @@ def test_emulator_predict(case):
         assert np.array_equal(cov, np.swapaxes(cov, 1, 2)) or scaled_err(cov, np.swapaxes(cov, 1, 2)) < 1e-15
         mean0 = emu.predict(Xin[:256], return_cov=False)
         assert rel_err(mean0, g["e%d_mean0" % e]) <= REL, name
+        md, vd = emu.predict_diag(Xin[:rows], extra_std=g["extra_std"][:rows])
+        assert rel_err(md, g["e%d_mean_x" % e]) <= REL and rel_err(vd, ref[:, d, d]) <= REL, name
         # scalar extra_std (the reference's default 0 breaks on NumPy 2; ours must not)
         # (a 4-row call uses a narrower walker tile than the 256-row one: same values up to
         # summation order)
