@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, "libgpbt_b200.so")
 
 KERNEL_RBF, KERNEL_MATERN32 = 0, 1
 FLAG_NO_PCA, FLAG_EXP_DIAG = 1, 2
-PATH_AUTO, PATH_DENSE, PATH_LOWRANK = 0, 1, 2
+PATH_AUTO, PATH_DENSE, PATH_LOWRANK, PATH_DIAG = 0, 1, 2, 3
 
 # every symbol include/gpbt.h declares (tests/test_cabi.py checks the library exports them all)
 SYMBOLS = [

@@ -77,11 +77,12 @@ struct gpbt_chain {
   std::vector<gpbt_emulator_t> emus;
   std::vector<int> q_off, m_off;
   int p, Q, M, device;
-  bool has_lowrank;
+  bool has_lowrank, has_diag;
   double s_perp, logdetF_half;
   double *lo, *hi, *y_exp, *cov_exp, *R, *c0;
   // workspaces (grown on demand)
-  int64_t cap_rows = 0, cap_dense = 0, cap_x = 0;
+  int64_t cap_rows = 0, cap_dense = 0, cap_x = 0, cap_diag = 0;
+  double *dmean = nullptr, *dvar = nullptr;
   double *z_mean = nullptr, *z_var = nullptr, *extra = nullptr, *mean = nullptr, *cov = nullptr;
   double *x_dev = nullptr, *lp_dev = nullptr;
   unsigned char* skip = nullptr;
@@ -308,6 +309,50 @@ __global__ void bounds_mask_kernel(const double* __restrict__ X, const double* _
   if (!ok) lp[w] = oob;
 }
 
+// Diagonal path: every emulator is no-PCA / exp-diag (diagonal model covariance, src/emulator.py:
+// 588-601) and expdata_cov is diagonal (as _read_in_exp_data_pickle builds it, src/mcmc.py:318-322):
+// the Cholesky of mvn_loglike (src/mcmc.py:23-65) degenerates to element-wise work.
+//   lp = -1/2 sum_o dy_o^2 / c_o - 1/2 sum_o log c_o + const,  c_o = var_o + sigma_exp_o^2
+// One warp per walker; applies the bounds mask like the other paths.
+__global__ void diag_loglike_kernel(const double* __restrict__ X, const double* __restrict__ lo,
+                                    const double* __restrict__ hi, int p, const double* __restrict__ mean,
+                                    const double* __restrict__ var, const double* __restrict__ y_exp,
+                                    const double* __restrict__ cov_exp, int M, int64_t N, double oob, double add_const,
+                                    double* __restrict__ lp, int* __restrict__ n_notpd) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= N) return;
+  bool ok = true;
+  for (int d = lane; d < p; d += 32) {
+    const double x = X[w * p + d];
+    ok = ok && (x > lo[d]) && (x < hi[d]);
+  }
+  if (!__all_sync(0xffffffffu, ok)) {
+    if (lane == 0) lp[w] = oob;
+    return;
+  }
+  double quad = 0.0, logdet = 0.0;
+  bool pd = true;
+  for (int o = lane; o < M; o += 32) {
+    const double c = var[w * M + o] + cov_exp[(size_t)o * M + o];
+    const double dy = mean[w * M + o] - y_exp[o];
+    pd = pd && (c > 0.0);
+    quad += dy * dy / c;
+    logdet += log(c);
+  }
+  quad = warp_sum(quad);
+  logdet = warp_sum(logdet);
+  pd = __all_sync(0xffffffffu, pd);
+  if (lane == 0) {
+    if (!pd) {
+      lp[w] = oob;
+      if (n_notpd) atomicAdd(n_notpd, 1);
+    } else {
+      lp[w] = -0.5 * quad - 0.5 * logdet + add_const;
+    }
+  }
+}
+
 // extra_std_arr = extra_std * X[:, -1]   (src/mcmc.py:157)
 __global__ void extra_std_kernel(const double* __restrict__ X, int p, int64_t N, double scale,
                                  double* __restrict__ out) {
@@ -395,6 +440,14 @@ extern "C" int gpbt_chain_create(gpbt_chain_t* out, const gpbt_emulator_t* emus,
   if (R && !all_pca) { delete ch; return fail(GPBT_ENOTAPPLICABLE, "low-rank factors given for a chain with a no-PCA / exp-diag emulator"); }
   if (R && !c0) { delete ch; return fail(GPBT_EINVAL, "R given without c0"); }
   ch->has_lowrank = R != nullptr;
+  bool all_diag = true;
+  for (int i = 0; i < n_emu; i++)
+    if (!(emus[i]->flags & (GPBT_FLAG_NO_PCA | GPBT_FLAG_EXP_DIAG))) all_diag = false;
+  bool exp_diag_only = true;
+  for (int r = 0; r < ch->M && exp_diag_only; r++)
+    for (int c2 = 0; c2 < ch->M; c2++)
+      if (r != c2 && cov_exp[(size_t)r * ch->M + c2] != 0.0) { exp_diag_only = false; break; }
+  ch->has_diag = all_diag && exp_diag_only;
   ch->s_perp = s_perp; ch->logdetF_half = logdetF_half;
   std::vector<double> h;
   h.assign(lo, lo + p); if (int r = upload(&ch->lo, h)) return r;
@@ -415,7 +468,7 @@ extern "C" int gpbt_chain_create(gpbt_chain_t* out, const gpbt_emulator_t* emus,
 extern "C" int gpbt_chain_destroy(gpbt_chain_t ch) {
   if (!ch) return 0;
   void* ptrs[] = {ch->lo, ch->hi, ch->y_exp, ch->cov_exp, ch->R, ch->c0, ch->z_mean, ch->z_var, ch->extra,
-                  ch->mean, ch->cov, ch->x_dev, ch->lp_dev, ch->skip, ch->notpd_dev};
+                  ch->mean, ch->cov, ch->x_dev, ch->lp_dev, ch->skip, ch->notpd_dev, ch->dmean, ch->dvar};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (ch->stream) cudaStreamDestroy(ch->stream);
@@ -514,7 +567,10 @@ extern "C" int gpbt_log_posterior(gpbt_chain_t ch, const double* X, double oob_v
   if (!ch || !X || !lp || N < 0) return fail(GPBT_EINVAL, "gpbt_log_posterior: bad argument");
   if (N == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  if (path == GPBT_PATH_AUTO) path = ch->has_lowrank ? GPBT_PATH_LOWRANK : GPBT_PATH_DENSE;
+  if (path == GPBT_PATH_AUTO)
+    path = ch->has_lowrank ? GPBT_PATH_LOWRANK : (ch->has_diag ? GPBT_PATH_DIAG : GPBT_PATH_DENSE);
+  if (path == GPBT_PATH_DIAG && !ch->has_diag)
+    return fail(GPBT_ENOTAPPLICABLE, "diagonal path requested but the covariance of this chain is not diagonal");
   if (path == GPBT_PATH_LOWRANK && !ch->has_lowrank)
     return fail(GPBT_ENOTAPPLICABLE, "low-rank path requested but the chain has no low-rank factors");
   if (n_notpd) CU(cudaMemsetAsync(n_notpd, 0, sizeof(int), st));
@@ -549,6 +605,36 @@ extern "C" int gpbt_log_posterior(gpbt_chain_t ch, const double* X, double oob_v
     }
     lowrank_loglike_kernel<<<grid, kLrWarps * 32, smem, st>>>(prm);
     LAUNCH_CHECK();
+    return 0;
+  }
+
+  if (path == GPBT_PATH_DIAG) {
+    // (a) -> mean + diag(cov) -> element-wise likelihood; workspace: mean/var [N, M]
+    const int64_t chunk = std::min<int64_t>(N, 1 << 18);
+    if (int r = ensure_rows(ch, chunk)) return r;
+    if (chunk > ch->cap_diag) {
+      if (ch->dmean) { cudaFree(ch->dmean); cudaFree(ch->dvar); }
+      CU(cudaMalloc(&ch->dmean, (size_t)chunk * ch->M * sizeof(double)));
+      CU(cudaMalloc(&ch->dvar, (size_t)chunk * ch->M * sizeof(double)));
+      ch->ws_bytes += (chunk - ch->cap_diag) * (int64_t)ch->M * 16;
+      ch->cap_diag = chunk;
+    }
+    for (int64_t s = 0; s < N; s += chunk) {
+      const int64_t nn = std::min(chunk, N - s);
+      const double* Xs = X + s * ch->p;
+      for (size_t e = 0; e < ch->emus.size(); e++) {
+        gpbt_emulator_t emu = ch->emus[e];
+        if (int r = run_pc_predict(emu, Xs, nullptr, ch->z_mean + ch->q_off[e], ch->z_var + ch->q_off[e], ch->Q, nn, st))
+          return r;
+        if (int r = run_backtransform(emu, ch->z_mean + ch->q_off[e], ch->z_var + ch->q_off[e], ch->Q, ch->dmean,
+                                      ch->M, nullptr, 0, ch->m_off[e], nn, st, ch->dvar))
+          return r;
+      }
+      diag_loglike_kernel<<<(unsigned)((nn * 32 + 255) / 256), 256, 0, st>>>(
+          Xs, ch->lo, ch->hi, ch->p, ch->dmean, ch->dvar, ch->y_exp, ch->cov_exp, ch->M, nn, oob_value, kSysConst,
+          lp + s, n_notpd);
+      LAUNCH_CHECK();
+    }
     return 0;
   }
 

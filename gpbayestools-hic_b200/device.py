@@ -183,7 +183,7 @@ class DeviceChain:
     @staticmethod
     def _path(path):
         return {None: _lib.PATH_AUTO, "auto": _lib.PATH_AUTO, "dense": _lib.PATH_DENSE,
-                "lowrank": _lib.PATH_LOWRANK}[path]
+                "lowrank": _lib.PATH_LOWRANK, "diag": _lib.PATH_DIAG}[path]
 
     def log_target(self, X, oob_value, path=None):
         """Host buffers in/out through gpbt_log_posterior_host (H2D, kernels, D2H, one sync)."""

@@ -37,7 +37,7 @@ typedef struct gpbt_chain* gpbt_chain_t;       /* emulators + experimental data 
 
 enum { GPBT_KERNEL_RBF = 0, GPBT_KERNEL_MATERN32 = 1 };
 enum { GPBT_FLAG_NO_PCA = 1, GPBT_FLAG_EXP_DIAG = 2 };
-enum { GPBT_PATH_AUTO = 0, GPBT_PATH_DENSE = 1, GPBT_PATH_LOWRANK = 2 };
+enum { GPBT_PATH_AUTO = 0, GPBT_PATH_DENSE = 1, GPBT_PATH_LOWRANK = 2, GPBT_PATH_DIAG = 3 };
 enum {
   GPBT_EINVAL = -1,   /* bad argument                                              */
   GPBT_ESHAPE = -2,   /* shape outside what the kernels support (message says why) */
@@ -124,12 +124,14 @@ int gpbt_chain_predict(gpbt_chain_t chain, const double* X_dev, double extra_std
 /* Chain.log_posterior / log_likelihood: bounds mask (strict, src/mcmc.py:275-276), emulators,
  * likelihood and the constant 2*log(1e-16) (src/mcmc.py:296-297).  Rows outside the box get
  * oob_value (-inf, or -1e300 for finite=True).  path: GPBT_PATH_AUTO picks LOWRANK when the
- * chain was created with R, else DENSE ((a) -> (b) -> (c) with the covariance in HBM).
+ * chain was created with R; DIAG (element-wise) when every emulator is no-PCA / exp-diag and
+ * cov_exp is diagonal; else DENSE ((a) -> (b) -> (c) with the covariance in HBM).  Asking for a
+ * path the chain cannot take returns GPBT_ENOTAPPLICABLE.
  * n_notpd_dev (may be NULL) counts non-positive-definite walkers.                            */
 int gpbt_log_posterior(gpbt_chain_t chain, const double* X_dev, double oob_value, double* lp_dev,
                        int* n_notpd_dev, int64_t N, int path, void* stream);
 
-/* Same with HOST buffers: pinned staging, H2D of X, kernels, D2H of lp, one synchronisation.
+/* Same with HOST buffers: H2D of X, kernels, D2H of lp, one synchronisation.
  * This is the call behind Chain.log_posterior(X: np.ndarray) -> np.ndarray.                  */
 int gpbt_log_posterior_host(gpbt_chain_t chain, const double* X_host, double oob_value,
                             double* lp_host, int* n_notpd_host, int64_t N, int path);

@@ -87,17 +87,20 @@ def test_chain_predict_and_mvn(case):
     ch.release()
 
 
-@pytest.mark.parametrize("path", ["lowrank", "dense"])
+@pytest.mark.parametrize("path", ["lowrank", "dense", "diag"])
 def test_log_posterior(case, path):
     """boundary #2: Chain.log_posterior / log_likelihood values and out-of-bounds conventions."""
     from gpbt_b200.device import DeviceChain
     name, g, states, sts = case
     ch = DeviceChain(states, g["lo"], g["hi"], g["y_exp"].reshape(-1), g["cov_exp"])
-    if path == "lowrank" and ch.lowrank is None:
+    diag_ok = all(s.no_pca or s.exp_diag for s in states)
+    if (path == "lowrank" and ch.lowrank is None) or (path == "diag" and not diag_ok):
         from gpbt_b200._lib import GpbtError
         with pytest.raises(GpbtError):
-            ch.log_target(g["X"], -np.inf, path="lowrank")
+            ch.log_target(g["X"], -np.inf, path=path)
         return
+    if path == "diag":   # ... and it is what "auto" picks for such chains
+        assert np.array_equal(ch.log_target(g["X"], -np.inf), ch.log_target(g["X"], -np.inf, path="diag"))
     ref = g["lp_posterior"]
     fin = np.isfinite(ref)
     lp = ch.log_target(g["X"], -np.inf, path=path)
@@ -113,6 +116,11 @@ def test_log_posterior(case, path):
     ch.release()
     # full (non-diagonal) experimental covariance, BASELINE config 4
     ch2 = DeviceChain(states, g["lo"], g["hi"], g["y_exp"].reshape(-1), goldens.cov_exp_sys(g))
+    if path == "diag":   # a full experimental covariance rules the element-wise path out
+        from gpbt_b200._lib import GpbtError
+        with pytest.raises(GpbtError):
+            ch2.log_target(g["X"], -np.inf, path="diag")
+        path = "dense"
     ls = ch2.log_target(g["X"], -np.inf, path=path)
     assert np.max(np.abs(ls[fin] - g["lp_posterior_sys"][fin])) <= ABS_LP, (name, path)
     ch2.release()
