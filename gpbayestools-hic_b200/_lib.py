@@ -15,6 +15,7 @@ PATH_AUTO, PATH_DENSE, PATH_LOWRANK, PATH_DIAG = 0, 1, 2, 3
 # every symbol include/gpbt.h declares (tests/test_cabi.py checks the library exports them all)
 SYMBOLS = [
     "gpbt_last_error", "gpbt_version", "gpbt_emulator_create", "gpbt_emulator_destroy",
+    "gpbt_emulator_set_param_trafo", "gpbt_emulator_input_dim",
     "gpbt_pc_predict", "gpbt_backtransform", "gpbt_backtransform_diag", "gpbt_mvn_loglike", "gpbt_chain_create",
     "gpbt_chain_destroy", "gpbt_chain_predict", "gpbt_log_posterior", "gpbt_log_posterior_host",
     "gpbt_chain_workspace_bytes", "gpbt_launch_count", "gpbt_debug_exp_neg",
@@ -37,6 +38,8 @@ def _load():
     lib.gpbt_launch_count.restype = i64
     lib.gpbt_emulator_create.argtypes = [C.POINTER(vp), i32, i32, i32, i32, i32, i32] + [dp] * 10
     lib.gpbt_emulator_destroy.argtypes = [vp]
+    lib.gpbt_emulator_set_param_trafo.argtypes = [vp, i32, dp, i32, i32, dp, dp, dp, dp, dp, dp, dp, dp]
+    lib.gpbt_emulator_input_dim.argtypes = [vp]
     lib.gpbt_pc_predict.argtypes = [vp, dp, dp, dp, dp, i64, i64, vp]
     lib.gpbt_backtransform.argtypes = [vp, dp, dp, i64, dp, i64, dp, i64, i64, i64, vp]
     lib.gpbt_backtransform_diag.argtypes = [vp, dp, dp, i64, dp, dp, i64, i64, i64, vp]
@@ -61,5 +64,5 @@ def check(rc):
 
 
 def host_ptr(a):
-    """pointer to a C-contiguous float64 numpy array (None -> NULL)"""
+    """pointer to a C-contiguous numpy array (None -> NULL)"""
     return None if a is None else a.ctypes.data_as(C.c_void_p)

@@ -14,6 +14,7 @@
 #include "chol_loglike.cuh"
 #include "common.cuh"
 #include "lowrank_loglike.cuh"
+#include "param_trafo.cuh"
 #include "pc_predict.cuh"
 
 using namespace gpbt;
@@ -71,6 +72,14 @@ int max_optin_smem() {
 struct gpbt_emulator {
   int p, p_pad, n, n_pad, q, q_pad, m, m_ld, kind, flags, device;
   double *Xs, *ell, *c, *sn, *W, *A, *mu, *scale, *Ctrunc;
+  // optional parameter-function PCA pre-transform: X [N, p_in] -> theta [N, p]
+  bool has_trafo;
+  int p_in;
+  ParamTrafoParams trafo;
+  int* keep_dev;
+  double* trafo_buf[2 * kPtMaxGroups];
+  double* theta;          // workspace [theta_cap, p]
+  int64_t theta_cap;
 };
 
 struct gpbt_chain {
@@ -164,8 +173,52 @@ extern "C" int gpbt_emulator_create(gpbt_emulator_t* out, int p, int n, int q, i
   return 0;
 }
 
+extern "C" int gpbt_emulator_set_param_trafo(gpbt_emulator_t e, int p_in, const int* keep, int n_keep,
+                                             int n_groups, const int* kinds, const int* idx, const int* ncomp,
+                                             const int* npts, const double* grid_lo, const double* grid_hi,
+                                             const double* const* Wt, const double* const* b) {
+  if (!e || !keep || n_groups < 1 || n_groups > kPtMaxGroups || !kinds || !idx || !ncomp || !npts || !Wt || !b)
+    return fail(GPBT_EINVAL, "gpbt_emulator_set_param_trafo: bad argument");
+  int p_out = n_keep;
+  for (int g = 0; g < n_groups; g++) p_out += ncomp[g];
+  if (p_out != e->p) return fail(GPBT_EINVAL, "param trafo produces %d columns, emulator was trained on %d", p_out, e->p);
+  ParamTrafoParams& T = e->trafo;
+  memset(&T, 0, sizeof T);
+  T.p_in = p_in; T.p_out = p_out; T.n_keep = n_keep; T.n_groups = n_groups;
+  std::vector<int> hk(keep, keep + n_keep);
+  if (int r = upload(&e->keep_dev, hk)) return r;
+  T.keep = e->keep_dev;
+  int off = n_keep;
+  for (int g = 0; g < n_groups; g++) {
+    ParamTrafoGroup& G = T.grp[g];
+    if (kinds[g] < 0 || kinds[g] > 2) return fail(GPBT_EINVAL, "unknown parametrisation kind %d", kinds[g]);
+    G.kind = kinds[g];
+    G.nargs = kinds[g] == 0 ? 4 : 3;
+    for (int i = 0; i < G.nargs; i++) {
+      G.idx[i] = idx[g * kPtMaxArgs + i];
+      if (G.idx[i] < 0 || G.idx[i] >= p_in) return fail(GPBT_EINVAL, "param trafo column %d outside X", G.idx[i]);
+    }
+    G.npts = npts[g]; G.ncomp = ncomp[g]; G.out_off = off; G.g0 = grid_lo[g]; G.g1 = grid_hi[g];
+    off += ncomp[g];
+    std::vector<double> hw(Wt[g], Wt[g] + (size_t)G.ncomp * G.npts), hb(b[g], b[g] + G.ncomp);
+    if (int r = upload(&e->trafo_buf[2 * g], hw)) return r;
+    if (int r = upload(&e->trafo_buf[2 * g + 1], hb)) return r;
+    G.Wt = e->trafo_buf[2 * g];
+    G.b = e->trafo_buf[2 * g + 1];
+  }
+  e->p_in = p_in;
+  e->has_trafo = true;
+  return 0;
+}
+
+extern "C" int gpbt_emulator_input_dim(gpbt_emulator_t e) { return e ? (e->has_trafo ? e->p_in : e->p) : 0; }
+
 extern "C" int gpbt_emulator_destroy(gpbt_emulator_t e) {
   if (!e) return 0;
+  if (e->keep_dev) cudaFree(e->keep_dev);
+  if (e->theta) cudaFree(e->theta);
+  for (double* p : e->trafo_buf)
+    if (p) cudaFree(p);
   double* ptrs[] = {e->Xs, e->ell, e->c, e->sn, e->W, e->A, e->mu, e->scale, e->Ctrunc};
   for (double* p : ptrs)
     if (p) cudaFree(p);
@@ -234,6 +287,20 @@ int dispatch_pc_predict(const PcPredictParams& prm, cudaStream_t st) {
 int run_pc_predict(gpbt_emulator_t e, const double* X, const double* extra, double* zm, double* zv,
                    int64_t ldz, int64_t N, cudaStream_t st) {
   if (N <= 0) return 0;
+  if (e->has_trafo) {
+    if (N > e->theta_cap) {
+      // (stream-ordered work that still reads the old buffer has been enqueued before this free;
+      // cudaFree synchronises the device)
+      if (e->theta) cudaFree(e->theta);
+      e->theta_cap = std::max<int64_t>(N, 2 * e->theta_cap);
+      CU(cudaMalloc(&e->theta, (size_t)e->theta_cap * e->p * sizeof(double)));
+    }
+    ParamTrafoParams T = e->trafo;
+    T.X = X; T.theta = e->theta; T.N = N;
+    param_trafo_kernel<<<(unsigned)((N * 32 + 127) / 128), 128, 0, st>>>(T);
+    LAUNCH_CHECK();
+    X = e->theta;
+  }
   PcPredictParams prm;
   prm.X = X; prm.extra = extra; prm.Xs = e->Xs; prm.ell = e->ell; prm.c = e->c; prm.sn = e->sn;
   prm.W = e->W; prm.z_mean = zm; prm.z_var = zv; prm.ldz = ldz; prm.N = N;
@@ -429,7 +496,10 @@ extern "C" int gpbt_chain_create(gpbt_chain_t* out, const gpbt_emulator_t* emus,
   cudaGetDevice(&ch->device);
   bool all_pca = true;
   for (int i = 0; i < n_emu; i++) {
-    if (!emus[i] || emus[i]->p != p) { delete ch; return fail(GPBT_EINVAL, "emulator %d: parameter count mismatch", i); }
+    if (!emus[i] || gpbt_emulator_input_dim(emus[i]) != p) {
+      delete ch;
+      return fail(GPBT_EINVAL, "emulator %d: parameter count mismatch", i);
+    }
     ch->emus.push_back(emus[i]);
     ch->q_off.push_back(ch->Q);
     ch->m_off.push_back(ch->M);

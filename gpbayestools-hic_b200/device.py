@@ -83,7 +83,7 @@ class DeviceEmulator:
         """NumPy in/out: (mean, var) with var = diag of the covariance predict() would return."""
         torch = _torch()
         st = self.state
-        X = as_rows(X, st.p)
+        X = as_rows(X, st.p_in)
         N = X.shape[0]
         extra = np.asarray(extra_std, dtype=np.float64).reshape(-1)
         if extra.size == 1:
@@ -102,7 +102,7 @@ class DeviceEmulator:
     def predict(self, X, return_cov=True, extra_std=0):
         torch = _torch()
         st = self.state
-        X = as_rows(X, st.p)
+        X = as_rows(X, st.p_in)
         N = X.shape[0]
         extra = np.asarray(extra_std, dtype=np.float64).reshape(-1)
         if extra.size == 1:
@@ -150,7 +150,7 @@ class DeviceChain:
 
     def __init__(self, states, lo, hi, y_exp, cov_exp, lowrank=True):
         self.states = list(states)
-        self.p = self.states[0].p
+        self.p = self.states[0].p_in   # columns of X (before any parameter-function pre-transform)
         self.M = sum(s.m for s in self.states)
         self.Q = sum(s.q for s in self.states)
         self.lo = np.ascontiguousarray(lo, dtype=np.float64).reshape(self.p)

@@ -47,6 +47,25 @@ def read_training_pickle(path, log_trafo=False, max_rel_uncertainty=0.1):
     return (np.array(design), np.array(data), np.nan_to_num(np.abs(np.array(err))), dropped)
 
 
+def curve_on_grid(kind, params, grid):
+    """The three parametrised curves of the reference evaluated on a grid, vectorised over rows of
+    `params` (src/emulator.py:100-124): kind 0 zeta/s(T; zeta_max, T_zeta0, sigma_plus, sigma_minus)
+    at mu_B = 0, kind 1 eta/s(mu_B; eta_0, eta_2, eta_4), kind 2 y_loss(y_init; yloss_2, _4, _6)."""
+    a = [np.asarray(params, dtype=np.float64)[:, i][:, None] for i in range(np.shape(params)[1])]
+    x = np.asarray(grid, dtype=np.float64)[None, :]
+    if kind == 0:
+        sig = np.where(x < a[1], a[3], a[2])
+        return a[0] * np.exp(-(x - a[1]) ** 2. / (2. * sig ** 2.))
+    if kind == 1:
+        return np.where((0. < x) & (x <= 0.2), a[0] + (a[1] - a[0]) * (x / 0.2),
+                        np.where((0.2 < x) & (x < 0.4), a[1] + (a[2] - a[1]) * ((x - 0.2) / 0.2), a[2] + 0. * x))
+    if kind == 2:
+        return np.where((0. < x) & (x <= 2.), a[0] * (x / 2.),
+                        np.where((2. < x) & (x < 4.), a[0] + (a[1] - a[0]) * ((x - 2.) / 2.),
+                                 a[1] + (a[2] - a[1]) * ((x - 4.) / 2.)))
+    raise ValueError(kind)
+
+
 class Emulator:
     """PCA + independent-GP emulator; same constructor and public methods as the reference class.
 
@@ -60,12 +79,8 @@ class Emulator:
         from sklearn.preprocessing import StandardScaler
         if exp_and_cov_diagonal and not logTrafo:
             raise ValueError("exp_and_cov_diagonal can only be set to True if logTrafo is True.")
-        if parameterTrafoPCA:
-            raise NotImplementedError(
-                "parameterTrafoPCA (src/emulator.py:79-99, 492-551) is a host pre-transform that "
-                "needs >= 19 parameters; it is outside this accelerated path (DESIGN.md, scope)")
         self.logTrafo_ = logTrafo
-        self.parameterTrafoPCA_ = False
+        self.parameterTrafoPCA_ = bool(parameterTrafoPCA)
         self.max_rel_uncertainty_data_ = max_rel_uncertainty_data
         self.exp_and_cov_diagonal_ = exp_and_cov_diagonal
         self.perform_no_PCA_ = perform_no_PCA
@@ -87,6 +102,40 @@ class Emulator:
         self.gps = []
         self._state = None
         self._device = None
+        if self.parameterTrafoPCA_:
+            self._fit_param_trafo()
+
+    # ---- parameter-function PCA (offline; the per-walker transform itself runs on the GPU) -----
+    def _fit_param_trafo(self, target_variance=0.99):
+        """Replace the zeta/s, eta/s and y_loss parameter groups of the design by the principal
+        components (99 % of the variance) of the curves they parametrise, in the reference's order
+        bulk -> shear -> y_loss, and move the design box along (src/emulator.py:79-99, 129-241)."""
+        from sklearn.decomposition import PCA
+        from sklearn.preprocessing import StandardScaler
+        from .state import PARAM_TRAFO_GROUPS
+        if self.design_points.shape[1] < 19:
+            raise ValueError("parameterTrafoPCA needs the 19+ parameter layout of the reference "
+                             "(columns 2-4, 12-14, 15-18 are the transformed groups)")
+        self.targetVariance = target_variance
+        self.indices_zeta_s_parameters = [15, 16, 17, 18]
+        self.indices_eta_s_parameters = [12, 13, 14]
+        self.indices_yloss_parameters = [2, 3, 4]
+        new_design = self.design_points
+        for kind, tag, idx_attr, grid in PARAM_TRAFO_GROUPS:
+            idx = getattr(self, idx_attr)
+            curves = curve_on_grid(kind, self.design_points[:, idx], np.linspace(*grid))
+            scaler = StandardScaler()
+            pca = PCA(n_components=target_variance)
+            pcs = pca.fit(scaler.fit_transform(curves)).transform(scaler.transform(curves))
+            setattr(self, "paramTrafoScaler_" + tag, scaler)
+            setattr(self, "paramTrafoPCA_" + tag, pca)
+            log.info("%s parameter PCA uses %d PCs", tag, pca.n_components_)
+            # indices refer to the ORIGINAL columns: groups are removed back to front (15-18, 12-14,
+            # 2-4), and the components are appended behind everything else
+            new_design = np.concatenate((np.delete(new_design, idx, axis=1), pcs), axis=1)
+            self.design_min = np.concatenate((np.delete(self.design_min, idx), pcs.min(axis=0)))
+            self.design_max = np.concatenate((np.delete(self.design_max, idx), pcs.max(axis=0)))
+        self.PCA_new_design_points = new_design
 
     # ---- training (offline, scikit-learn, as the reference) -----------------------------------
     def trainEmulatorAutoMask(self):
@@ -114,7 +163,7 @@ class Emulator:
             Z = self.pca.fit_transform(Y)[:, :self.npc]
             log.info("%d PCs explain %.5f of variance", self.npc,
                      self.pca.explained_variance_ratio_[:self.npc].sum())
-        theta = self.design_points[mask, :]
+        theta = (self.PCA_new_design_points if self.parameterTrafoPCA_ else self.design_points)[mask, :]
         kernel = self._make_kernel(kernel_type)
         self.gps = [GaussianProcessRegressor(kernel=kernel, alpha=GPR_ALPHA,
                                              n_restarts_optimizer=self.nrestarts,
@@ -155,7 +204,7 @@ class Emulator:
         """An Emulator that only predicts (no training data), around an existing state."""
         self = cls.__new__(cls)
         self.logTrafo_ = state.exp_diag
-        self.parameterTrafoPCA_ = False
+        self.parameterTrafoPCA_ = state.trafo is not None
         self.exp_and_cov_diagonal_ = state.exp_diag
         self.perform_no_PCA_ = state.no_pca
         self.npc, self.nobs, self.nev = state.q, state.m, state.n

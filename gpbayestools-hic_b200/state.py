@@ -75,6 +75,52 @@ def _kernel_kind_and_hypers(kernel):
         float(white.noise_level)
 
 
+# (kind, attribute suffix on the reference object, index attribute, grid) of the three parameter
+# groups of "parameterTrafoPCA" in the order the reference applies them (src/emulator.py:79-99, 492-551)
+PARAM_TRAFO_GROUPS = (
+    (0, "bulk", "indices_zeta_s_parameters", (0.0, 0.5, 100)),
+    (1, "shear", "indices_eta_s_parameters", (0.0, 0.6, 100)),
+    (2, "yloss", "indices_yloss_parameters", (0.0, 6.2, 100)),
+)
+
+
+@dataclass
+class ParamTrafo:
+    """The parameter-function PCA pre-transform of one emulator, as plain arrays.
+    groups[i] = dict(kind, idx [nargs], grid (lo, hi, npts), smean [npts], sscale [npts],
+                     pmean [npts], comp [ncomp, npts])"""
+    p_in: int
+    groups: list
+
+    @property
+    def keep(self):
+        used = {int(c) for g in self.groups for c in g["idx"]}
+        return np.array([c for c in range(self.p_in) if c not in used], dtype=np.int32)
+
+    @property
+    def p_out(self):
+        return len(self.keep) + sum(g["comp"].shape[0] for g in self.groups)
+
+    @classmethod
+    def from_trained(cls, emu):
+        groups = []
+        for kind, tag, idx_attr, grid in PARAM_TRAFO_GROUPS:
+            sc, pc = getattr(emu, "paramTrafoScaler_" + tag), getattr(emu, "paramTrafoPCA_" + tag)
+            groups.append(dict(kind=kind, idx=np.asarray(getattr(emu, idx_attr), dtype=np.int32), grid=grid,
+                               smean=_f64(sc.mean_), sscale=_f64(sc.scale_), pmean=_f64(pc.mean_),
+                               comp=_f64(pc.components_)))
+        return cls(p_in=int(np.asarray(emu.design_points_org_).shape[1]), groups=groups)
+
+    def folded(self):
+        """(Wt [ncomp, npts], b [ncomp]) per group:  PC = f @ Wt.T + b  ==  PCA.transform(Scaler.transform(f))"""
+        out = []
+        for g in self.groups:
+            Wt = np.ascontiguousarray(g["comp"] / g["sscale"])
+            b = -(g["comp"] @ (g["smean"] / g["sscale"] + g["pmean"]))
+            out.append((Wt, np.ascontiguousarray(b)))
+        return out
+
+
 @dataclass
 class EmulatorState:
     kind: str                 # "RBF" | "Matern"
@@ -91,11 +137,14 @@ class EmulatorState:
     no_pca: bool = False
     exp_diag: bool = False
     L: Optional[np.ndarray] = None        # [q, n, n] kept only for oracle comparisons
+    trafo: Optional[ParamTrafo] = None    # parameterTrafoPCA pre-transform (then p counts transformed columns)
     _handle: Optional[C.c_void_p] = field(default=None, repr=False, compare=False)
 
     # ---- shapes ---------------------------------------------------------------------------
     @property
     def p(self): return self.Xtr.shape[1]
+    @property
+    def p_in(self): return self.trafo.p_in if self.trafo is not None else self.Xtr.shape[1]
     @property
     def n(self): return self.Xtr.shape[0]
     @property
@@ -106,7 +155,7 @@ class EmulatorState:
     # ---- constructors ---------------------------------------------------------------------
     @classmethod
     def from_arrays(cls, kind, Xtr, ell, c, sn, alpha, mu, scale, A=None, Ctrunc=None, L=None,
-                    no_pca=False, exp_diag=False, keep_L=True):
+                    no_pca=False, exp_diag=False, keep_L=True, trafo=None):
         Xtr, alpha = _f64(Xtr), _f64(alpha)
         q, n = alpha.shape
         ell = _f64(np.broadcast_to(np.asarray(ell, dtype=np.float64).reshape(q, -1), (q, Xtr.shape[1])))
@@ -118,7 +167,7 @@ class EmulatorState:
         return cls(kind=str(kind), Xtr=Xtr, ell=ell, c=c, sn=sn, alpha=alpha, Linv=_f64(Linv),
                    mu=_f64(mu), scale=_f64(scale), A=None if A is None else _f64(A),
                    Ctrunc=None if Ctrunc is None else _f64(Ctrunc), no_pca=bool(no_pca),
-                   exp_diag=bool(exp_diag), L=L if keep_L else None)
+                   exp_diag=bool(exp_diag), L=L if keep_L else None, trafo=trafo)
 
     @classmethod
     def from_trained(cls, emu, keep_L=False):
@@ -126,10 +175,7 @@ class EmulatorState:
         GPRs), `scaler`, `npc`, `_trans_matrix`, `_cov_trunc`, `perform_no_PCA_`,
         `exp_and_cov_diagonal_` -- i.e. a dill-loaded reference `src.emulator.Emulator` or this
         package's `Emulator`."""
-        if getattr(emu, "parameterTrafoPCA_", False):
-            raise NotImplementedError(
-                "parameterTrafoPCA emulators need the host pre-transform (src/emulator.py:492-551); "
-                "not on the accelerated path yet")
+        trafo = ParamTrafo.from_trained(emu) if getattr(emu, "parameterTrafoPCA_", False) else None
         gps = emu.gps
         hyp = [_kernel_kind_and_hypers(g.kernel_) for g in gps]
         kinds = {h[0] for h in hyp}
@@ -147,7 +193,7 @@ class EmulatorState:
             A=None if no_pca else emu._trans_matrix[:emu.npc],
             Ctrunc=None if no_pca else emu._cov_trunc,
             L=np.stack([g.L_ for g in gps]), no_pca=no_pca,
-            exp_diag=bool(getattr(emu, "exp_and_cov_diagonal_", False)), keep_L=keep_L)
+            exp_diag=bool(getattr(emu, "exp_and_cov_diagonal_", False)), keep_L=keep_L, trafo=trafo)
 
     # ---- views ----------------------------------------------------------------------------
     def oracle_dict(self):
@@ -158,6 +204,8 @@ class EmulatorState:
                  L=self.L, no_pca=self.no_pca, exp_diag=self.exp_diag, mu=self.mu, scale=self.scale)
         if not self.no_pca:
             d.update(A=self.A, Ctrunc=self.Ctrunc)
+        if self.trafo is not None:
+            d["trafo"] = dict(p_in=self.trafo.p_in, groups=self.trafo.groups)
         return d
 
     def device_bytes(self):
@@ -177,6 +225,24 @@ class EmulatorState:
                 C.byref(h), self.p, self.n, self.q, self.m, kind, flags, hp(self.Xtr), hp(self.ell),
                 hp(self.c), hp(self.sn), hp(self.alpha), hp(self.Linv), hp(self.A), hp(self.mu),
                 hp(self.scale), hp(self.Ctrunc)))
+            if self.trafo is not None:
+                t = self.trafo
+                ng = len(t.groups)
+                keep = t.keep
+                kinds = np.array([g["kind"] for g in t.groups], dtype=np.int32)
+                idx = np.zeros((ng, 4), dtype=np.int32)
+                for i, g in enumerate(t.groups):
+                    idx[i, :len(g["idx"])] = g["idx"]
+                ncomp = np.array([g["comp"].shape[0] for g in t.groups], dtype=np.int32)
+                npts = np.array([g["grid"][2] for g in t.groups], dtype=np.int32)
+                glo = np.array([g["grid"][0] for g in t.groups], dtype=np.float64)
+                ghi = np.array([g["grid"][1] for g in t.groups], dtype=np.float64)
+                folded = t.folded()
+                Wt = (C.c_void_p * ng)(*[hp(w) for w, _ in folded])
+                bb = (C.c_void_p * ng)(*[hp(b) for _, b in folded])
+                _lib.check(_lib.lib.gpbt_emulator_set_param_trafo(
+                    h, t.p_in, hp(keep), len(keep), ng, hp(kinds), hp(idx), hp(ncomp), hp(npts), hp(glo), hp(ghi),
+                    C.cast(Wt, C.c_void_p), C.cast(bb, C.c_void_p)))
             self._handle = h
         return self._handle
 

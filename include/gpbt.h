@@ -64,6 +64,23 @@ int gpbt_emulator_create(gpbt_emulator_t* out, int p, int n, int q, int m, int k
                          const double* scale_host, const double* Ctrunc_host);
 int gpbt_emulator_destroy(gpbt_emulator_t emu);
 
+/* Optional "parameterTrafoPCA" pre-transform in front of kernel (a) (src/emulator.py:492-551,
+ * src/emulator_BAND.py:393-452): walkers arrive with p_in model parameters; the columns listed in
+ * `keep` are copied through, and each of n_groups (<= 3) parameter groups is replaced by ncomp[g]
+ * principal components of the npts[g]-point curve it parametrises on linspace(grid_lo, grid_hi):
+ *   kind 0  zeta/s(T)       4 columns  (src/emulator.py:100-106)
+ *   kind 1  eta/s(mu_B)     3 columns  (src/emulator.py:109-115)
+ *   kind 2  y_loss(y_init)  3 columns  (src/emulator.py:118-124)
+ * idx is [n_groups][4]; Wt[g] is [ncomp[g]][npts[g]] and b[g] is [ncomp[g]], the StandardScaler and
+ * PCA of the reference folded into  PC_j = sum_t f_t Wt[j][t] + b_j.  n_keep + sum(ncomp) must
+ * equal the p the emulator was created with.  All pointers are HOST pointers.                 */
+int gpbt_emulator_set_param_trafo(gpbt_emulator_t emu, int p_in, const int* keep, int n_keep,
+                                  int n_groups, const int* kinds, const int* idx, const int* ncomp,
+                                  const int* npts, const double* grid_lo, const double* grid_hi,
+                                  const double* const* Wt, const double* const* b);
+/* number of columns of X this emulator expects (p_in with a pre-transform, else p)              */
+int gpbt_emulator_input_dim(gpbt_emulator_t emu);
+
 /* ---- kernel (a): per-(walker, PC) cross-kernel + GP mean + predictive variance ----------- *
  * Replaces [gp.predict(X, return_cov=True) for gp in self.gps] + diagonal extraction + the
  * extra_std**2 term (src/emulator.py:553, 573-579; sklearn _gpr.py:446-466).

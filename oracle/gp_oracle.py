@@ -13,6 +13,7 @@ It is a plain NumPy/SciPy restatement of what the reference computes between
   sklearn kernels.py Matern nu=1.5     (:1713-1729)      kernel_cross(kind="Matern")
   sklearn _gpr.py predict              (:446-475)        gp_predict_pc
   src/emulator.py Emulator.predict     (:465-605)        emulator_predict
+  src/emulator.py parameterTrafoPCA    (:100-124,492-551) param_trafo
   src/emulator.py _inverse_transform   (:366-375)        emulator_predict (PCA branch)
   src/mcmc.py Chain._predict           (:153-166)        chain_predict
   src/mcmc.py mvn_loglike              (:23-65)          mvn_loglike
@@ -71,9 +72,50 @@ def gp_predict_pc(state, j, X):
     return mean, var
 
 
+def _zeta_over_s(zeta_max, T_zeta0, sigma_plus, sigma_minus, T, mu_B=0.0):
+    """src/emulator.py:100-106"""
+    T_zeta_muB = T_zeta0 - 0.15 * mu_B ** 2.
+    sig = np.where(T < T_zeta0, sigma_minus, sigma_plus)
+    return zeta_max * np.exp(-(T - T_zeta_muB) ** 2. / (2. * sig ** 2.))
+
+
+def _eta_over_s(eta_0, eta_2, eta_4, mu_B):
+    """src/emulator.py:109-115"""
+    return np.where((0. < mu_B) & (mu_B <= 0.2), eta_0 + (eta_2 - eta_0) * (mu_B / 0.2),
+                    np.where((0.2 < mu_B) & (mu_B < 0.4), eta_2 + (eta_4 - eta_2) * ((mu_B - 0.2) / 0.2), eta_4))
+
+
+def _y_loss(yloss_2, yloss_4, yloss_6, y_init):
+    """src/emulator.py:118-124"""
+    return np.where((0. < y_init) & (y_init <= 2.), yloss_2 * (y_init / 2.),
+                    np.where((2. < y_init) & (y_init < 4.), yloss_2 + (yloss_4 - yloss_2) * ((y_init - 2.) / 2.),
+                             yloss_4 + (yloss_6 - yloss_4) * ((y_init - 4.) / 2.)))
+
+
+_CURVES = {0: _zeta_over_s, 1: _eta_over_s, 2: _y_loss}
+
+
+def param_trafo(trafo, X):
+    """The parameterTrafoPCA pre-transform inside Emulator.predict (src/emulator.py:492-551):
+    curves on their grids -> StandardScaler.transform -> PCA.transform; untouched columns first, then
+    the bulk, shear and y_loss components."""
+    X = np.asarray(X, dtype=np.float64)
+    used = {int(c) for g in trafo["groups"] for c in g["idx"]}
+    cols = [X[:, [c for c in range(trafo["p_in"]) if c not in used]]]
+    for g in trafo["groups"]:
+        grid = np.linspace(*g["grid"])
+        args = [X[:, int(c)][:, None] for c in g["idx"]]
+        f = _CURVES[int(g["kind"])](*args, grid[None, :])
+        scaled = (f - g["smean"]) / g["sscale"]
+        cols.append((scaled - g["pmean"]) @ g["comp"].T)
+    return np.concatenate(cols, axis=1)
+
+
 def pc_predict(state, X, extra_std=None):
     """z_mean[N,q], z_var[N,q] for all GPs; z_var includes extra_std**2 (src/emulator.py:573-579)."""
     X = np.asarray(X, dtype=np.float64)
+    if state.get("trafo") is not None:
+        X = param_trafo(state["trafo"], X)
     q = state["alpha"].shape[0]
     zm = np.empty((X.shape[0], q))
     zv = np.empty((X.shape[0], q))
@@ -85,7 +127,8 @@ def pc_predict(state, X, extra_std=None):
 
 
 def emulator_predict(state, X, return_cov=True, extra_std=None):
-    """Emulator.predict (src/emulator.py:465-605) without the parameterTrafoPCA pre-transform."""
+    """Emulator.predict (src/emulator.py:465-605); the parameterTrafoPCA pre-transform is applied in
+    pc_predict when the state carries one."""
     X = np.asarray(X, dtype=np.float64)
     zm, zv = pc_predict(state, X, extra_std)
     if not state["no_pca"]:

@@ -76,8 +76,20 @@ def extract_state(emu, kind, prefix=""):
     return {prefix + k: v for k, v in st.items()}
 
 
+def trafo_arrays(emu, prefix):
+    """scalers / PCAs of the reference's parameterTrafoPCA (src/emulator.py:79-99, 129-241)"""
+    out = {prefix + "trafo_p_in": np.array(emu.design_points_org_.shape[1])}
+    for tag, idx in (("bulk", emu.indices_zeta_s_parameters), ("shear", emu.indices_eta_s_parameters),
+                     ("yloss", emu.indices_yloss_parameters)):
+        sc, pc = getattr(emu, "paramTrafoScaler_" + tag), getattr(emu, "paramTrafoPCA_" + tag)
+        out.update({prefix + "trafo_%s_idx" % tag: np.array(idx), prefix + "trafo_%s_smean" % tag: sc.mean_,
+                    prefix + "trafo_%s_sscale" % tag: sc.scale_, prefix + "trafo_%s_pmean" % tag: pc.mean_,
+                    prefix + "trafo_%s_comp" % tag: pc.components_})
+    return out
+
+
 def make_case(name, syn, Emulator, Chain, mvn_loglike, p, n, emus, N, seed, keep_cov_rows,
-              store_L=True, extra_std_scale=0.05):
+              store_L=True, extra_std_scale=0.05, shift=0.0):
     """emus: list of dicts(m, q, kind, logTrafo, exp_diag, no_pca). One Chain over all of them."""
     import dill
     import pickle
@@ -87,9 +99,18 @@ def make_case(name, syn, Emulator, Chain, mvn_loglike, p, n, emus, N, seed, keep
     # one simulator with m_total observables; each emulator trains on its slice of them
     full = syn.training_dict(p, n, m_total)
     exp = syn.experiment_dict(p, m_total)
+    par_text = syn.parameter_file_text(p)
+    if shift:
+        # keep every coordinate away from 0 (the zeta/s widths sigma_+- of parameterTrafoPCA divide):
+        # the whole box moves by `shift`, the simulator still sees the unshifted coordinates
+        for v in full.values():
+            v["parameter"] = v["parameter"] + shift
+        lo_, hi_ = syn.box(p)
+        par_text = "".join("par%d: p%d, %r, %r\n" % (d, d, float(lo_[d] + shift), float(hi_[d] + shift))
+                           for d in range(p))
     par_path = os.path.join(wd, "par.txt")
     with open(par_path, "w") as f:
-        f.write(syn.parameter_file_text(p))
+        f.write(par_text)
     exp_path = os.path.join(wd, "exp.pkl")
     with open(exp_path, "wb") as f:
         pickle.dump(exp, f)
@@ -106,7 +127,8 @@ def make_case(name, syn, Emulator, Chain, mvn_loglike, p, n, emus, N, seed, keep
         emu = Emulator(training_set_path=tp, parameter_file=par_path, npc=e["q"],
                        logTrafo=e.get("logTrafo", False),
                        exp_and_cov_diagonal=e.get("exp_diag", False),
-                       perform_no_PCA=e.get("no_pca", False))
+                       perform_no_PCA=e.get("no_pca", False),
+                       parameterTrafoPCA=e.get("param_trafo", False))
         emu.trainEmulator([True] * emu.nev, kernel_type=e["kind"])
         ep = os.path.join(wd, "emu%d.pkl" % e_i)
         with open(ep, "wb") as f:
@@ -117,9 +139,12 @@ def make_case(name, syn, Emulator, Chain, mvn_loglike, p, n, emus, N, seed, keep
         if not store_L:
             st.pop("e%d_Lpacked" % e_i)
         out.update(st)
+        if e.get("param_trafo", False):
+            out.update(trafo_arrays(emu, "e%d_" % e_i))
 
-    X = syn.walkers(p, N, seed=seed)
+    X = syn.walkers(p, N, seed=seed) + shift
     lo, hi = syn.box(p)
+    lo, hi = lo + shift, hi + shift
     inside = np.all((X > lo) & (X < hi), axis=1)
     Xin = X[inside]
     out.update(X=X, lo=lo, hi=hi, inside=inside)
@@ -130,6 +155,15 @@ def make_case(name, syn, Emulator, Chain, mvn_loglike, p, n, emus, N, seed, keep
     out["extra_std"] = extra
     for e_i, emu in enumerate(ref_emus):
         # per-GP sklearn outputs (PC space): mean and diag of the predictive covariance
+        # (not for parameterTrafoPCA emulators: their GPs live in the transformed parameter space and
+        # the reference has no stand-alone transform to feed them with)
+        if getattr(emu, "parameterTrafoPCA_", False):
+            rows = Xin[:max(keep_cov_rows, 1)]
+            mean, cov = emu.predict(rows, return_cov=True, extra_std=extra[:len(rows)])
+            out["e%d_mean_x" % e_i] = mean
+            out["e%d_cov_x" % e_i] = cov
+            out["e%d_mean0" % e_i] = emu.predict(Xin[:256], return_cov=False)
+            continue
         zm = np.stack([g.predict(Xin, return_cov=False) for g in emu.gps], axis=1)
         if len(Xin) <= 512:
             zv = np.stack([g.predict(Xin, return_cov=True)[1].diagonal() for g in emu.gps], axis=1)
@@ -182,7 +216,10 @@ CASES = {
     "c1_nopca": (5, 100, [dict(m=12, q=12, kind="RBF", no_pca=True)], 64, 6, 8),
     "c1_multi": (5, 100, [dict(m=30, q=8, kind="RBF"), dict(m=20, q=6, kind="Matern")], 64, 7, 8),
     "odd_shape": (3, 37, [dict(m=13, q=5, kind="RBF")], 33, 8, 8),
+    # 20 parameters with the reference's parameterTrafoPCA groups (columns 2-4, 12-14, 15-18)
+    "p20_trafo": (20, 90, [dict(m=16, q=6, kind="RBF", param_trafo=True)], 64, 9, 8),
 }
+SHIFT = {"p20_trafo": 0.05}
 C2_CASE = {"c2_rbf": (17, 500, [dict(m=300, q=20, kind="RBF")], 1024, 3, 1)}
 
 
@@ -201,7 +238,7 @@ def main():
         if only and name not in only:
             continue
         make_case(name, syn, Emulator, Chain, mvn_loglike, p, n, emus, N, seed, keep,
-                  store_L=(n <= 100))
+                  store_L=(n <= 100), shift=SHIFT.get(name, 0.0))
 
 
 if __name__ == "__main__":

@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-SMALL_CASES = ["c1_rbf", "c1_matern", "c1_logexp", "c1_nopca", "c1_multi", "odd_shape"]
+SMALL_CASES = ["c1_rbf", "c1_matern", "c1_logexp", "c1_nopca", "c1_multi", "odd_shape", "p20_trafo"]
 
 
 def available():
@@ -59,6 +59,13 @@ def oracle_states(g):
         if not st["no_pca"]:
             st["A"] = g[pre + "A"]
             st["Ctrunc"] = g[pre + "Ctrunc"]
+        if pre + "trafo_p_in" in g:
+            grids = {"bulk": (0, (0.0, 0.5, 100)), "shear": (1, (0.0, 0.6, 100)), "yloss": (2, (0.0, 6.2, 100))}
+            st["trafo"] = dict(p_in=int(g[pre + "trafo_p_in"]), groups=[
+                dict(kind=grids[t][0], grid=grids[t][1], idx=g[pre + "trafo_%s_idx" % t],
+                     smean=g[pre + "trafo_%s_smean" % t], sscale=g[pre + "trafo_%s_sscale" % t],
+                     pmean=g[pre + "trafo_%s_pmean" % t], comp=g[pre + "trafo_%s_comp" % t])
+                for t in ("bulk", "shear", "yloss")])
         states.append(st)
     return states
 

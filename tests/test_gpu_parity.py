@@ -25,6 +25,14 @@ def test_pc_predict(case):
     name, g, states, sts = case
     Xin = np.ascontiguousarray(g["X"][g["inside"]])
     for e, (st, ost) in enumerate(zip(states, sts)):
+        if st.trafo is not None:
+            # the device applies the parameter-function pre-transform itself; PC-space values are
+            # compared with the oracle (the reference pins this case through observable-space outputs)
+            zm, zv = DeviceEmulator(st).pc_predict_device(torch.from_numpy(Xin).cuda())
+            om, ov = orc.pc_predict(ost, Xin)
+            assert rel_err(zv.cpu().numpy(), ov) <= REL
+            assert np.max(np.abs(zm.cpu().numpy() - om) / pc_scale(ost, Xin)) <= 1e-12
+            continue
         zm, zv = DeviceEmulator(st).pc_predict_device(torch.from_numpy(Xin).cuda())
         zm, zv = zm.cpu().numpy(), zv.cpu().numpy()
         # variance: 1e-9 relative (it already contains the k** - |L^-1 k|^2 cancellation)
@@ -209,3 +217,39 @@ def test_exp_accuracy():
     ulp = np.abs(y[ok] - ref[ok]) / np.spacing(ref[ok])
     assert ulp.max() <= 1.0, ulp.max()
     assert np.all(y[~ok] == 0.0) and y[len(x) - 7] == 1.0
+
+
+def test_param_trafo_drop_in(tmp_path):
+    """parameterTrafoPCA end to end with this package's Emulator: host fit of the three curve PCAs,
+    device pre-transform kernel, Chain.log_posterior -- against the oracle (whose pre-transform is
+    pinned to the reference by the p20_trafo golden)."""
+    import pickle
+    from gpbt_b200 import synthetic
+    from gpbt_b200.emulator import Emulator
+    from gpbt_b200.mcmc import Chain
+    p, n, m, shift = 20, 70, 12, 0.05
+    paths = synthetic.write_fixture(str(tmp_path), p=p, n=n, m=m)
+    with open(paths["train"], "rb") as fh:
+        tr = pickle.load(fh)
+    for v in tr.values():
+        v["parameter"] = v["parameter"] + shift
+    with open(paths["train"], "wb") as fh:
+        pickle.dump(tr, fh)
+    lo, hi = synthetic.box(p)
+    with open(paths["par"], "w") as fh:
+        fh.write("".join("par%d: p%d, %r, %r\n" % (d, d, float(lo[d] + shift), float(hi[d] + shift)) for d in range(p)))
+    emu = Emulator(training_set_path=paths["train"], parameter_file=paths["par"], npc=5, parameterTrafoPCA=True)
+    emu.trainEmulatorAutoMask()
+    assert emu.state.trafo is not None and emu.state.p == emu.PCA_new_design_points.shape[1] < p
+    (tmp_path / "mcmc").mkdir()
+    ch = Chain(mcmc_path=str(tmp_path / "mcmc" / "chain.pkl"), expdata_path=paths["exp"], model_parafile=paths["par"])
+    ch.emuList = [emu]
+    X = synthetic.walkers(p, 150, seed=21) + shift
+    lp = ch.log_posterior(X)
+    want = orc.log_posterior([emu.state.oracle_dict()], X, ch.min, ch.max, ch.expdata, ch.expdata_cov)
+    fin = np.isfinite(want)
+    assert np.array_equal(np.isneginf(lp), np.isneginf(want)) and fin.sum() > 100
+    assert np.max(np.abs(lp[fin] - want[fin])) <= ABS_LP
+    mean, cov = emu.predict(X[fin][:5], return_cov=True)
+    omean, ocov = orc.emulator_predict(emu.state.oracle_dict(), X[fin][:5], True)
+    assert rel_err(mean, omean) <= REL and scaled_err(cov, ocov) <= REL

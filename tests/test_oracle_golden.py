@@ -22,6 +22,8 @@ def test_pc_space(case):
     g = goldens.load(case)
     Xin = g["X"][g["inside"]]
     for e, st in enumerate(goldens.oracle_states(g)):
+        if "e%d_z_mean" % e not in g:
+            continue   # parameterTrafoPCA case: pinned through the observable-space outputs only
         zm, zv = orc.pc_predict(st, Xin)
         # PC-space means are ill-conditioned sums: compare against the scale of the
         # summands, not of the (possibly cancelling) result
