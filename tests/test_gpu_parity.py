@@ -191,6 +191,14 @@ def test_invariances():
             assert np.max(np.abs(ch.log_target(X[:700], -np.inf) - lp[:700])) <= 1e-10, tile
     finally:
         os.environ.pop("GPBT_PC_TILE", None)
+    # both Cholesky kernels (warp-per-walker for small m, CTA-per-walker otherwise) agree
+    dense0 = ch.log_target(X[:300], -np.inf, path="dense")
+    try:
+        for which in ("warp", "cta"):
+            os.environ["GPBT_CHOL"] = which
+            assert np.max(np.abs(ch.log_target(X[:300], -np.inf, path="dense") - dense0)) <= 1e-9, which
+    finally:
+        os.environ.pop("GPBT_CHOL", None)
     # the shared-memory low-rank kernel (fallback for Q > 32) agrees with the register one
     try:
         os.environ["GPBT_LOWRANK_GENERIC"] = "1"
