@@ -295,6 +295,14 @@ def run_ours(args):
 
     line = None
     if rank == 0:
+        # DRAM traffic of the dominant kernel per launch, from the committed ncu capture
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_pc_predict_traffic.json")) as fh:
+                tj = json.load(fh)
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+        except (OSError, KeyError, ValueError):
+            pass
         # FP64 roofline denominator: cuBLAS DGEMM, measured here
         n = 8192 if args.dgemm else 0
         peak, peak_src = 35.45, "profiles/r01_dgemm_peak.json (cuBLAS DGEMM 8192^3 on this pool)"
@@ -355,7 +363,11 @@ def run_ours(args):
             "wall_ms_per_step_incl_flush": 1e3 * t_wall / K,
             "clocks": clk.summary(),
             "roofline": {"kernel": "pc_predict_kernel (a)", "bound": "tensor", "achieved": achieved, "peak": peak,
-                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                         "traffic_note": "dram read+write bytes per launch (ncu, profiles/r01_pc_predict_traffic.json); "
+                                         "algorithmic HBM bytes are 8p in + 16q out = 456 B per evaluation (1.9 MB per launch): "
+                                         "the rest is the 21 MB lower triangle of L^-1 streamed once into L2",
+                         "hbm_achieved_GBps": (traffic or 0) / (ka_ms * 1e-3) / 1e9,
                          "peak_source": peak_src, "ms_per_launch": ka_ms,
                          "algorithmic_flops_per_eval": flops_pc_predict(SHAPE["p"], SHAPE["n"], SHAPE["q"]),
                          "dtype": "FP64 DMMA.8x8x4 + DFMA (one shared pipe, 37.1 TFLOP/s DMMA issue peak measured)"},
