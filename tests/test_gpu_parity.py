@@ -261,3 +261,32 @@ def test_param_trafo_drop_in(tmp_path):
     mean, cov = emu.predict(X[fin][:5], return_cov=True)
     omean, ocov = orc.emulator_predict(emu.state.oracle_dict(), X[fin][:5], True)
     assert rel_err(mean, omean) <= REL and scaled_err(cov, ocov) <= REL
+
+
+def test_full_size_properties():
+    """BASELINE config 4 scale (2^17 walkers per call, config-2 emulator, full experimental
+    covariance): size-independent properties -- chunking invariance against 4096-row calls,
+    out-of-bounds bookkeeping, and an oracle spot check on random rows."""
+    from gpbt_b200 import synthetic
+    from gpbt_b200.device import DeviceChain
+    if "c2_rbf" not in goldens.available():
+        pytest.skip("config-2 golden missing")
+    g = goldens.load("c2_rbf")
+    states, sts = product_states(g)
+    cov = goldens.cov_exp_sys(g)
+    ch = DeviceChain(states, g["lo"], g["hi"], g["y_exp"].reshape(-1), cov)
+    N = 1 << 17
+    rng = np.random.default_rng(123)
+    X = rng.uniform(g["lo"], g["hi"], (N, len(g["lo"])))
+    out = rng.choice(N, N // 100, replace=False)
+    X[out, 0] = g["hi"][0] + 1.0
+    lp = ch.log_target(X, -1e300)
+    assert lp.shape == (N,) and np.count_nonzero(lp == -1e300) == len(out) and np.all(lp[out] == -1e300)
+    assert not np.any(np.isnan(lp)) and ch.last_notpd == 0
+    for s in (0, 40960, N - 4096):
+        part = ch.log_target(X[s:s + 4096], -1e300)
+        assert np.max(np.abs(part - lp[s:s + 4096])) <= 1e-9
+    rows = rng.choice(N, 24, replace=False)
+    want = orc.log_likelihood(sts, X[rows], g["lo"], g["hi"], g["y_exp"], cov, finite=True)
+    assert np.max(np.abs(lp[rows] - want)) <= ABS_LP
+    ch.release()
