@@ -84,9 +84,14 @@ __global__ void __launch_bounds__(128) backtransform_mean_kernel(const Backtrans
 // For an item, D[i][j] = Ctrunc[i][j] + sum_k (v_k A[k][i]) * A[k][j]: the accumulators are
 // initialised with the Ctrunc tile (its L2 latency overlaps the other warps' tensor work), the
 // A-operand fragment (row i = g, k = t) and the B-operand fragment (k = t, col j = g) both come from
-// the same [q_pad][m_ld] array (m_ld = 4 mod 8 keeps those loads bank-conflict free), and every
-// lane stores its two adjacent columns with one 16-byte store (64-byte row segments per quad).
-// The n8 column blocks of a row tile are dealt to the 4 warps as contiguous ranges.
+// the same [q_pad][m_ld] array (m_ld = 4 mod 8 keeps those loads bank-conflict free).
+// cov is symmetric, so an item only computes the column blocks at or right of its diagonal tile and
+// stores every off-diagonal 8x8 block twice: directly (16-byte stores, 64-byte row segments per
+// quad) and mirrored (lanes of equal t write 8 consecutive doubles of a row).  That halves the
+// tensor work, which otherwise is as large as the HBM write stream (both ~30 k cycles per walker
+// per SM at q = 20, m = 300).  The n8 column blocks of an item are dealt to the 4 warps as
+// contiguous ranges; the grid size is chosen coprime to the number of row tiles so that the
+// round-robin hands every CTA all tile sizes.
 constexpr int kBtThreads = 128;
 constexpr int kBtWarps = kBtThreads / 32;
 constexpr int kBtRows = 32;
@@ -95,7 +100,7 @@ inline size_t backtransform_smem_bytes(int q_pad, int m_ld) {
   return sizeof(double) * ((size_t)q_pad * m_ld + 2 * (size_t)q_pad * kBtRows);
 }
 
-__global__ void __launch_bounds__(kBtThreads, 4) backtransform_cov_kernel(const BacktransformParams prm, int q_pad) {
+__global__ void __launch_bounds__(kBtThreads, 3) backtransform_cov_kernel(const BacktransformParams prm, int q_pad) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int m = prm.m, m_ld = prm.m_ld;
   double* As = reinterpret_cast<double*>(smem_raw);  // [q_pad][m_ld]
@@ -113,15 +118,14 @@ __global__ void __launch_bounds__(kBtThreads, 4) backtransform_cov_kernel(const 
   const int64_t n_items = prm.N * n_rt;
   const int64_t ldc = prm.ld_cov, off = prm.col_off;
   const bool vec_ok = (ldc % 2 == 0) && (off % 2 == 0) && ((reinterpret_cast<uintptr_t>(prm.cov) & 15) == 0);
-  // contiguous range of n8 column blocks for this warp
+  const bool ct_vec = (m % 2 == 0) && ((reinterpret_cast<uintptr_t>(prm.Ctrunc) & 15) == 0);
   const int n_nb = (m + 7) / 8;
-  const int nb_per = (n_nb + kBtWarps - 1) / kBtWarps;
-  const int nb_lo = min(warp * nb_per, n_nb), nb_hi = min(nb_lo + nb_per, n_nb);
 
   int buf = 0;
   for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, buf ^= 1) {
     const int64_t w = item / n_rt;
-    const int i0 = (int)(item - w * n_rt) * kBtRows;
+    const int rt = (int)(item - w * n_rt);
+    const int i0 = rt * kBtRows;
     double* av = Av + (size_t)buf * q_pad * kBtRows;
     for (int idx = tid; idx < q_pad * kBtRows; idx += kBtThreads) {
       const int k = idx / kBtRows, r = idx - k * kBtRows;
@@ -129,7 +133,11 @@ __global__ void __launch_bounds__(kBtThreads, 4) backtransform_cov_kernel(const 
       av[idx] = (i0 + r < m) ? v * As[(size_t)k * m_ld + i0 + r] : 0.0;
     }
     __syncthreads();  // (double buffered: the previous item's readers of the other buffer are done)
-    double* out = prm.cov + ((size_t)w * ldc + off + i0) * ldc + off;
+    double* wbase = prm.cov + (size_t)w * ldc * ldc + (size_t)off * ldc + off;  // block (0,0) of this emulator
+    // column blocks 4*rt .. n_nb-1 of this item over the 4 warps
+    const int nb_first = 4 * rt, nb_cnt = n_nb - nb_first;
+    const int nb_per = (nb_cnt + kBtWarps - 1) / kBtWarps;
+    const int nb_lo = min(nb_first + warp * nb_per, n_nb), nb_hi = min(nb_lo + nb_per, n_nb);
     for (int nb0 = nb_lo; nb0 < nb_hi; nb0 += 4) {
       double acc[4][4][2];
       // accumulators start from the Ctrunc tile; lane owns D[8mb + g][8nb + 2t + {0,1}]
@@ -140,8 +148,14 @@ __global__ void __launch_bounds__(kBtThreads, 4) backtransform_cov_kernel(const 
         for (int nb = 0; nb < 4; nb++) {
           const int j = 8 * (nb0 + nb) + 2 * t;
           const bool in = (i < m) && (nb0 + nb < nb_hi);
-          acc[mb][nb][0] = (in && j < m) ? __ldg(prm.Ctrunc + (size_t)i * m + j) : 0.0;
-          acc[mb][nb][1] = (in && j + 1 < m) ? __ldg(prm.Ctrunc + (size_t)i * m + j + 1) : 0.0;
+          if (in && ct_vec && j + 1 < m) {
+            const double2 c2 = ldg2(prm.Ctrunc + (size_t)i * m + j);
+            acc[mb][nb][0] = c2.x;
+            acc[mb][nb][1] = c2.y;
+          } else {
+            acc[mb][nb][0] = (in && j < m) ? __ldg(prm.Ctrunc + (size_t)i * m + j) : 0.0;
+            acc[mb][nb][1] = (in && j + 1 < m) ? __ldg(prm.Ctrunc + (size_t)i * m + j + 1) : 0.0;
+          }
         }
       }
       for (int k0 = 0; k0 < q_pad; k0 += 4) {
@@ -162,17 +176,23 @@ __global__ void __launch_bounds__(kBtThreads, 4) backtransform_cov_kernel(const 
       }
 #pragma unroll
       for (int mb = 0; mb < 4; mb++) {
-        if (i0 + 8 * mb + g >= m) continue;
-        double* row = out + (size_t)(8 * mb + g) * ldc;
+        const int i = i0 + 8 * mb + g;
+        if (i >= m) continue;
 #pragma unroll
         for (int nb = 0; nb < 4; nb++) {
           const int j = 8 * (nb0 + nb) + 2 * t;
           if (nb0 + nb >= nb_hi || j >= m) continue;
+          double* row = wbase + (size_t)i * ldc;
           if (vec_ok && j + 1 < m) {
             *reinterpret_cast<double2*>(row + j) = make_double2(acc[mb][nb][0], acc[mb][nb][1]);
           } else {
             row[j] = acc[mb][nb][0];
             if (j + 1 < m) row[j + 1] = acc[mb][nb][1];
+          }
+          // mirror of the blocks right of the diagonal 32x32 tile: cov[j][i] = cov[i][j]
+          if (nb0 + nb >= nb_first + 4) {
+            wbase[(size_t)j * ldc + i] = acc[mb][nb][0];
+            if (j + 1 < m) wbase[(size_t)(j + 1) * ldc + i] = acc[mb][nb][1];
           }
         }
       }
