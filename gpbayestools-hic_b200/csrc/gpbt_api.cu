@@ -61,11 +61,37 @@ int upload(T** dst, const std::vector<T>& v) {
   return 0;
 }
 
-int max_optin_smem() {
-  int dev = 0, v = 0;
+constexpr int kMaxDevices = 64;
+
+int current_device() {
+  int dev = 0;
   cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  return v;
+  return dev;
+}
+
+int max_optin_smem() {
+  static int cache[kMaxDevices] = {0};
+  const int dev = current_device();
+  if (dev < 0 || dev >= kMaxDevices) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    return v;
+  }
+  if (cache[dev] == 0) cudaDeviceGetAttribute(&cache[dev], cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  return cache[dev];
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device setting: remember the largest size
+// configured for each kernel on each device (the kernel is a template argument, so every kernel --
+// every instantiation of a kernel template -- has its own table)
+template <auto Kernel>
+int ensure_dynamic_smem(size_t bytes) {
+  static size_t configured[kMaxDevices] = {0};
+  const int dev = current_device();
+  if (dev >= 0 && dev < kMaxDevices && bytes <= configured[dev]) return 0;
+  CU(cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  if (dev >= 0 && dev < kMaxDevices) configured[dev] = bytes;
+  return 0;
 }
 
 }  // namespace
@@ -235,11 +261,7 @@ namespace {
 template <int TW, int KIND, int P2>
 int launch_pc_predict(const PcPredictParams& prm, cudaStream_t st) {
   const size_t smem = pc_predict_smem_bytes<TW>(prm.n_pad, prm.p_pad);
-  static size_t configured = 0;
-  if (smem > configured) {
-    CU(cudaFuncSetAttribute(pc_predict_kernel<TW, KIND, P2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  if (int r = ensure_dynamic_smem<pc_predict_kernel<TW, KIND, P2>>(smem)) return r;
   dim3 grid((unsigned)((prm.N + TW - 1) / TW), (unsigned)prm.q);
   pc_predict_kernel<TW, KIND, P2><<<grid, kPcThreads, smem, st>>>(prm);
   LAUNCH_CHECK();
@@ -326,11 +348,7 @@ int run_backtransform(gpbt_emulator_t e, const double* zm, const double* zv, int
     const size_t smem = backtransform_smem_bytes(e->q_pad, e->m_ld);
     if (smem > (size_t)max_optin_smem())
       return fail(GPBT_ESHAPE, "backtransform: q*m = %d*%d does not fit in shared memory", e->q, e->m);
-    static size_t configured = 0;
-    if (smem > configured) {
-      CU(cudaFuncSetAttribute(backtransform_cov_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
-    }
+    if (int r = ensure_dynamic_smem<backtransform_cov_kernel>(smem)) return r;
     const int64_t items = N * ((e->m + kBtRows - 1) / kBtRows);
     int per_sm = (int)std::min<size_t>(3, (228 * 1024 - 4096) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
@@ -365,11 +383,7 @@ int run_chol(const double* mean, const double* y_exp, double* cov, const double*
   if (which && which[0] == 'w') use_warp = true;
   if (which && which[0] == 'c') use_warp = false;
   if (use_warp && wsmem <= (size_t)max_optin_smem()) {
-    static size_t wconfigured = 0;
-    if (wsmem > wconfigured) {
-      CU(cudaFuncSetAttribute(chol_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
-      wconfigured = wsmem;
-    }
+    if (int r = ensure_dynamic_smem<chol_warp_kernel>(wsmem)) return r;
     chol_warp_kernel<<<(unsigned)N, 32, wsmem, st>>>(prm);
     LAUNCH_CHECK();
     return 0;
@@ -377,11 +391,7 @@ int run_chol(const double* mean, const double* y_exp, double* cov, const double*
   const size_t smem = chol_smem_bytes(m);
   if (smem > (size_t)max_optin_smem())
     return fail(GPBT_ESHAPE, "mvn_loglike: m = %d observables exceed the shared-memory panel", m);
-  static size_t configured = 0;
-  if (smem > configured) {
-    CU(cudaFuncSetAttribute(chol_loglike_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  if (int r = ensure_dynamic_smem<chol_loglike_kernel>(smem)) return r;
   chol_loglike_kernel<<<(unsigned)N, kChThreads, smem, st>>>(prm);
   LAUNCH_CHECK();
   return 0;
@@ -474,6 +484,8 @@ extern "C" int gpbt_debug_exp_neg(const double* x, double* y, int64_t n, void* s
 extern "C" int gpbt_pc_predict(gpbt_emulator_t emu, const double* X, const double* extra, double* zm,
                                double* zv, int64_t ldz, int64_t N, void* stream) {
   if (!emu || !X || !zm || !zv || ldz < emu->q || N < 0) return fail(GPBT_EINVAL, "gpbt_pc_predict: bad argument");
+  if (emu->device != current_device())
+    return fail(GPBT_EINVAL, "emulator lives on device %d, current device is %d", emu->device, current_device());
   return run_pc_predict(emu, X, extra, zm, zv, ldz, N, (cudaStream_t)stream);
 }
 
@@ -661,6 +673,8 @@ extern "C" int gpbt_chain_predict(gpbt_chain_t ch, const double* X, double extra
 extern "C" int gpbt_log_posterior(gpbt_chain_t ch, const double* X, double oob_value, double* lp, int* n_notpd,
                                   int64_t N, int path, void* stream) {
   if (!ch || !X || !lp || N < 0) return fail(GPBT_EINVAL, "gpbt_log_posterior: bad argument");
+  if (ch->device != current_device())
+    return fail(GPBT_EINVAL, "chain lives on device %d, current device is %d", ch->device, current_device());
   if (N == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   if (path == GPBT_PATH_AUTO)
@@ -694,11 +708,7 @@ extern "C" int gpbt_log_posterior(gpbt_chain_t ch, const double* X, double oob_v
     }
     const size_t smem = lowrank_smem_bytes(ch->Q);
     if (smem > (size_t)max_optin_smem()) return fail(GPBT_ESHAPE, "low-rank path: Q = %d too large", ch->Q);
-    static size_t configured = 0;
-    if (smem > configured) {
-      CU(cudaFuncSetAttribute(lowrank_loglike_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
-    }
+    if (int r = ensure_dynamic_smem<lowrank_loglike_kernel>(smem)) return r;
     lowrank_loglike_kernel<<<grid, kLrWarps * 32, smem, st>>>(prm);
     LAUNCH_CHECK();
     return 0;

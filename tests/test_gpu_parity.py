@@ -290,3 +290,37 @@ def test_full_size_properties():
     want = orc.log_likelihood(sts, X[rows], g["lo"], g["hi"], g["y_exp"], cov, finite=True)
     assert np.max(np.abs(lp[rows] - want)) <= ABS_LP
     ch.release()
+
+
+def test_sampler_drives_gpu_posterior(tmp_path, monkeypatch):
+    """Sampler smoke: Chain.run_mcmc with an emcee-compatible ensemble sampler
+    (tests/fake_emcee.py: emcee is not installed) -- pool=self hands whole half-ensembles to the GPU
+    log_posterior, the chain file has the reference's layout, walkers stay inside the box and the
+    stored positions re-evaluate to finite posteriors."""
+    import pickle
+    import sys
+    from tests import fake_emcee
+    from gpbt_b200.mcmc import Chain
+    monkeypatch.setitem(sys.modules, "emcee", fake_emcee)
+    g = goldens.load("c1_rbf")
+    states, sts = product_states(g)
+    (tmp_path / "mcmc").mkdir()
+    from gpbt_b200 import synthetic
+    paths = synthetic.write_fixture(str(tmp_path), p=5, n=8, m=50)
+    ch = Chain(mcmc_path=str(tmp_path / "mcmc" / "chain.pkl"), expdata_path=paths["exp"], model_parafile=paths["par"])
+    ch.emuList = states                       # EmulatorState objects are accepted directly
+    np.random.seed(0)
+    ch.run_mcmc(nsteps=12, nburnsteps=8, nwalkers=16, nthin=3)
+    with open(ch.mcmc_path, "rb") as fh:
+        stored = pickle.load(fh)
+    chain = stored["chain"]
+    assert chain.shape == (16, 4, 5)          # [walker, thinned step, dim]
+    flat = chain.reshape(-1, 5)
+    assert np.all((flat > ch.min) & (flat < ch.max))
+    lp = ch.log_posterior(flat)
+    assert np.all(np.isfinite(lp))
+    want = orc.log_posterior(sts, flat[:12], ch.min, ch.max, ch.expdata, ch.expdata_cov)
+    assert np.max(np.abs(lp[:12] - want)) <= ABS_LP
+    ch.run_mcmc(nsteps=6, nburnsteps=8, nwalkers=16, nthin=3)          # restart from the stored chain
+    with open(ch.mcmc_path, "rb") as fh:
+        assert pickle.load(fh)["chain"].shape == (16, 6, 5)

@@ -1,0 +1,133 @@
+"""CPU tests of the host-side logic that feeds the kernels: the exact low-rank factors
+(device.lowrank_factors) against the dense mvn_loglike of the oracle, state extraction from trained
+sklearn objects, the parameter-function curves, and pickling."""
+import numpy as np
+import pytest
+from hypothesis import given, settings
+from hypothesis import strategies as st
+
+from oracle import gp_oracle as orc
+from tests import goldens
+from tests.helpers import product_states
+
+
+def _fake_states(rng, m_list, q_list):
+    import gpbt_b200  # noqa: F401
+    from types import SimpleNamespace
+    out = []
+    for m, q in zip(m_list, q_list):
+        B = rng.normal(size=(m + 3, m))
+        out.append(SimpleNamespace(m=m, q=q, A=rng.normal(size=(q, m)), mu=rng.normal(size=m) + 3.0,
+                                   Ctrunc=B.T @ B / m + 0.05 * np.eye(m), no_pca=False, exp_diag=False))
+    return out
+
+
+@settings(max_examples=25, deadline=None)
+@given(seed=st.integers(0, 10 ** 6), n_emu=st.integers(1, 3), full=st.booleans(), scale=st.floats(0.01, 30.0))
+def test_lowrank_identity_matches_dense(seed, n_emu, full, scale):
+    """log det / quadratic form through (R, c0, s_perp, logdetF) == dpotrf/dpotrs on the assembled
+    covariance (src/mcmc.py:23-65), for random chains, with a diagonal or a full experimental
+    covariance, and PC variances spanning small to large (scale)."""
+    from gpbt_b200.device import lowrank_factors
+    rng = np.random.default_rng(seed)
+    m_list = [int(rng.integers(3, 9)) for _ in range(n_emu)]
+    q_list = [int(rng.integers(1, mm)) for mm in m_list]
+    states = _fake_states(rng, m_list, q_list)
+    M, Q = sum(m_list), sum(q_list)
+    y_exp = rng.normal(size=M) + 3.0
+    cov_exp = np.diag(rng.uniform(0.01, 0.2, M))
+    if full:
+        G = 0.1 * rng.normal(size=(M, 2))
+        cov_exp = cov_exp + G @ G.T
+    lr = lowrank_factors(states, y_exp, cov_exp)
+    assert lr["R"].shape == (Q, Q) and np.allclose(lr["R"], np.triu(lr["R"]))
+    for _ in range(3):
+        z = rng.normal(size=Q)
+        v = scale * rng.uniform(1e-4, 1.0, Q)
+        # dense reference: block-diagonal model covariance + experimental covariance
+        C = cov_exp.copy()
+        mean = np.empty(M)
+        qo = mo = 0
+        for s in states:
+            C[mo:mo + s.m, mo:mo + s.m] += (s.A.T * v[qo:qo + s.q]) @ s.A + s.Ctrunc
+            mean[mo:mo + s.m] = z[qo:qo + s.q] @ s.A + s.mu
+            qo += s.q
+            mo += s.m
+        want = orc.mvn_loglike(mean - y_exp, C)
+        c = lr["R"] @ z + lr["c0"]
+        S = np.eye(Q) + (lr["R"] * v) @ lr["R"].T
+        Ls = np.linalg.cholesky(S)
+        t = np.linalg.solve(Ls, c)
+        got = -0.5 * (lr["s_perp"] + t @ t) - np.log(np.diag(Ls)).sum() - lr["logdetF_half"]
+        assert abs(got - want) <= 1e-9 * max(1.0, abs(want))
+
+
+def test_state_from_trained_matches_golden_arrays(tmp_path):
+    """EmulatorState.from_trained on this package's Emulator reproduces what it was trained to:
+    L Linv = I, oracle predictions from the extracted state equal sklearn's own per-GP predict."""
+    import gpbt_b200  # noqa: F401
+    from gpbt_b200 import synthetic
+    from gpbt_b200.emulator import Emulator
+    paths = synthetic.write_fixture(str(tmp_path), p=3, n=40, m=10)
+    for kind in ("RBF", "Matern"):
+        emu = Emulator(training_set_path=paths["train"], parameter_file=paths["par"], npc=4)
+        emu.trainEmulator([True] * emu.nev, kernel_type=kind)
+        stt = emu.state
+        assert stt.kind == kind and stt.p == 3 and stt.n == 40 and stt.q == 4 and stt.m == 10
+        for j in range(stt.q):
+            assert np.max(np.abs(stt.Linv[j] @ stt.L[j] - np.eye(stt.n))) < 1e-10
+        X = synthetic.walkers(3, 20, seed=4, frac_outside=0.0)
+        zm, zv = orc.pc_predict(stt.oracle_dict(), X)
+        for j, gp in enumerate(emu.gps):
+            mu_j, cov_j = gp.predict(X, return_cov=True)
+            assert np.max(np.abs(zm[:, j] - mu_j)) < 1e-9 and np.max(np.abs(zv[:, j] - cov_j.diagonal())) < 1e-9
+        # the pickled emulator carries no device handle and still knows its state
+        import dill
+        emu2 = dill.loads(dill.dumps(emu))
+        assert emu2._device is None and emu2.state.q == 4
+
+
+def test_curves_match_reference_piecewise_definitions():
+    """curve_on_grid against a literal scalar transcription of src/emulator.py:100-124."""
+    import gpbt_b200  # noqa: F401
+    from gpbt_b200.emulator import curve_on_grid
+
+    def zeta(a, T):
+        sig = a[3] if T < a[1] else a[2]
+        return a[0] * np.exp(-(T - a[1]) ** 2. / (2. * sig ** 2.))
+
+    def eta(a, x):
+        if 0. < x <= 0.2:
+            return a[0] + (a[1] - a[0]) * (x / 0.2)
+        if 0.2 < x < 0.4:
+            return a[1] + (a[2] - a[1]) * ((x - 0.2) / 0.2)
+        return a[2]
+
+    def yl(a, y):
+        if 0. < y <= 2.:
+            return a[0] * (y / 2.)
+        if 2. < y < 4.:
+            return a[0] + (a[1] - a[0]) * ((y - 2.) / 2.)
+        return a[1] + (a[2] - a[1]) * ((y - 4.) / 2.)
+
+    rng = np.random.default_rng(3)
+    for kind, fn, nargs, grid in ((0, zeta, 4, np.linspace(0, .5, 100)), (1, eta, 3, np.linspace(0, .6, 100)),
+                                  (2, yl, 3, np.linspace(0, 6.2, 100))):
+        P = rng.uniform(0.05, 1.0, (7, nargs))
+        got = curve_on_grid(kind, P, grid)
+        want = np.array([[fn(row, x) for x in grid] for row in P])
+        assert np.allclose(got, want, rtol=0, atol=1e-15)
+        # the oracle's vectorised copies agree too
+        o = orc._CURVES[kind](*[P[:, i][:, None] for i in range(nargs)], grid[None, :])
+        assert np.allclose(o, want, rtol=0, atol=1e-15)
+
+
+def test_golden_states_are_consistent():
+    """alpha_ and L_ in the golden files belong together: L L^T alpha reproduces sklearn's training
+    targets up to the PCA whitening (unit variance) -- guards against mixing up fixture arrays."""
+    g = goldens.load("c1_rbf")
+    states, sts = product_states(g)
+    s = sts[0]
+    y = np.stack([s["L"][j] @ (s["L"][j].T @ s["alpha"][j]) for j in range(len(s["c"]))])
+    assert np.all(np.abs(y.std(axis=1) - 1.0) < 0.05) and np.all(np.abs(y.mean(axis=1)) < 1e-8)
+    assert states[0].device_bytes() > 0
