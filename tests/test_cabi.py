@@ -67,3 +67,17 @@ def test_no_cpu_fallback_without_gpu(lib):
     ch = DeviceChain(states, g["lo"], g["hi"], g["y_exp"].reshape(-1), g["cov_exp"])
     with pytest.raises(RuntimeError):
         ch.log_target(g["X"], -np.inf)
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/gpbt.h is a C header (no C++-isms): a C translation unit that includes it compiles."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "use_gpbt.c"
+    src.write_text('#include "gpbt.h"\nint main(void) { gpbt_chain_t c = 0; gpbt_emulator_t e = 0; (void)c; (void)e; return GPBT_PATH_AUTO; }\n')
+    res = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
