@@ -324,3 +324,28 @@ def test_sampler_drives_gpu_posterior(tmp_path, monkeypatch):
     ch.run_mcmc(nsteps=6, nburnsteps=8, nwalkers=16, nthin=3)          # restart from the stored chain
     with open(ch.mcmc_path, "rb") as fh:
         assert pickle.load(fh)["chain"].shape == (16, 6, 5)
+
+
+def test_n1000_shape():
+    """BASELINE config 3's shape (15 parameters, 1000 design points) with a GP emulator of that size:
+    the design no longer fits a 32-walker tile (kernel (a) falls back to one 16-walker CTA per SM) and
+    L^-1 no longer fits L2 -- values against the oracle.  (The surmise PCSK emulator of config 3 itself
+    has no oracle here: parity unpinned.)"""
+    from gpbt_b200 import synthetic
+    from gpbt_b200.device import DeviceChain
+    from gpbt_b200.state import EmulatorState
+    arr = synthetic.untrained_state_arrays(15, 1000, 40, 6)
+    st = EmulatorState.from_arrays(**arr, keep_L=True)
+    lo, hi = synthetic.box(15)
+    y_exp = synthetic.Simulator(15, 40)(lo + 0.4 * (hi - lo))[0]
+    cov_exp = np.diag((0.03 * np.abs(y_exp)) ** 2)
+    ch = DeviceChain([st], lo, hi, y_exp, cov_exp)
+    X = synthetic.walkers(15, 600, seed=9)
+    lp = ch.log_target(X, -np.inf)
+    rows = np.r_[0:24, 576:600]
+    want = orc.log_posterior([st.oracle_dict()], X[rows], lo, hi, y_exp.reshape(1, -1), cov_exp)
+    fin = np.isfinite(want)
+    assert np.array_equal(np.isneginf(lp[rows]), ~fin)
+    assert np.max(np.abs(lp[rows][fin] - want[fin])) <= ABS_LP
+    assert np.max(np.abs(ch.log_target(X[:64], -np.inf, path="dense") - lp[:64])[np.isfinite(lp[:64])]) <= ABS_LP
+    ch.release()
