@@ -220,6 +220,20 @@ def run_ours(args):
     Xh = [torch.from_numpy(walkers(g, N, 1000 * rank + i)).pin_memory() for i in range(nb)]
     Xd = [x.to(dev) for x in Xh]
     ev = ShardedEvaluator(lambda X: chain.log_target_device(X, -np.inf, path=args.path), dev)
+    # multi-GPU: the all-gather of lp is fused into the last kernel (NVLink peer stores + one device
+    # barrier); NCCL all-gather is the fallback (--collective nccl, or symmetric memory unavailable)
+    collective = "none"
+    gather_fn = ev.evaluate_local
+    if world > 1:
+        collective = "nccl all-gather of lp (8 B/walker)"
+        if args.collective == "fused":
+            try:
+                from gpbt_b200.dist import PeerGather
+                pg = PeerGather(N, dev)
+                gather_fn = lambda X: pg.evaluate(chain, X, -np.inf, path=args.path)   # noqa: E731
+                collective = "fused: peer stores from the last kernel over NVLink + device barrier"
+            except Exception as exc:   # symmetric memory not available on this box
+                collective += " (fused unavailable: %s)" % type(exc).__name__
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def barrier():
@@ -237,7 +251,7 @@ def run_ours(args):
 
     # ---- device-resident leg -------------------------------------------------------------
     for i in range(W):
-        ev.evaluate_local(Xd[i])
+        gather_fn(Xd[i])
     barrier()
     launches0 = _lib.lib.gpbt_launch_count()
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
@@ -247,7 +261,7 @@ def run_ours(args):
         for i in range(K):
             flush.fill_(i & 0xff)
             ev0[i].record()
-            out = ev.evaluate_local(Xd[W + i])
+            out = gather_fn(Xd[W + i])
             ev1[i].record()
         barrier()
         t_wall = time.perf_counter() - t_wall0
@@ -263,7 +277,7 @@ def run_ours(args):
         if world == 1:
             return chain.log_target(Xh[i].numpy(), -np.inf, path=args.path)      # gpbt_log_posterior_host
         xd = Xh[i].to(dev, non_blocking=True)
-        lp_host.copy_(ev.evaluate_local(xd), non_blocking=True)
+        lp_host.copy_(gather_fn(xd), non_blocking=True)
         torch.cuda.synchronize()
         return lp_host.numpy()
 
@@ -356,7 +370,7 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "walkers_per_gpu_per_step": N, "path": args.path,
                        "state": "hyper-parameters trained by the reference (tests/golden/c2_rbf.npz)",
                        "l2": "256 MB flush between timed steps, outside the CUDA events",
-                       "collective": "all-gather of lp (8 B/walker)" if world > 1 else "none"},
+                       "collective": collective},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N * p * 8,
                     "d2h_bytes_per_step": world * N * 8, "ms_per_step": 1e3 * e2e_s / K},
             "gpu_launches": int(launches),
@@ -393,6 +407,7 @@ def main():
     ap.add_argument("--dense-steps", type=int, default=3)
     ap.add_argument("--dense-walkers", type=int, default=2048)
     ap.add_argument("--no-dgemm", dest="dgemm", action="store_false")
+    ap.add_argument("--collective", default="fused", choices=["fused", "nccl"])
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -17,7 +17,8 @@ SYMBOLS = [
     "gpbt_last_error", "gpbt_version", "gpbt_emulator_create", "gpbt_emulator_destroy",
     "gpbt_emulator_set_param_trafo", "gpbt_emulator_input_dim",
     "gpbt_pc_predict", "gpbt_backtransform", "gpbt_backtransform_diag", "gpbt_mvn_loglike", "gpbt_chain_create",
-    "gpbt_chain_destroy", "gpbt_chain_predict", "gpbt_log_posterior", "gpbt_log_posterior_host",
+    "gpbt_chain_destroy", "gpbt_chain_predict", "gpbt_log_posterior", "gpbt_log_posterior_scatter",
+    "gpbt_log_posterior_host",
     "gpbt_chain_workspace_bytes", "gpbt_launch_count", "gpbt_debug_exp_neg",
 ]
 
@@ -48,6 +49,7 @@ def _load():
     lib.gpbt_chain_destroy.argtypes = [vp]
     lib.gpbt_chain_predict.argtypes = [vp, dp, dbl, dp, dp, i64, vp]
     lib.gpbt_log_posterior.argtypes = [vp, dp, dbl, dp, dp, i64, i32, vp]
+    lib.gpbt_log_posterior_scatter.argtypes = [vp, dp, dbl, dp, dp, i32, i64, dp, i64, i32, vp]
     lib.gpbt_log_posterior_host.argtypes = [vp, dp, dbl, dp, dp, i64, i32]
     lib.gpbt_debug_exp_neg.argtypes = [dp, dp, i64, vp]
     lib.gpbt_chain_workspace_bytes.argtypes = [vp]

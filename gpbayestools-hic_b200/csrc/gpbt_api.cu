@@ -456,6 +456,19 @@ __global__ void diag_loglike_kernel(const double* __restrict__ X, const double* 
   }
 }
 
+// copy a finished result vector into the peer-mapped buffers of the other GPUs (paths whose last
+// kernel does not store to peers itself)
+struct PeerList {
+  double* p[kMaxPeers];
+  int n;
+};
+__global__ void scatter_to_peers_kernel(const double* __restrict__ src, PeerList peers, int64_t off, int64_t N) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= N) return;
+  const double v = src[w];
+  for (int r = 0; r < peers.n; r++) peers.p[r][off + w] = v;
+}
+
 // extra_std_arr = extra_std * X[:, -1]   (src/mcmc.py:157)
 __global__ void extra_std_kernel(const double* __restrict__ X, int p, int64_t N, double scale,
                                  double* __restrict__ out) {
@@ -670,8 +683,37 @@ extern "C" int gpbt_chain_predict(gpbt_chain_t ch, const double* X, double extra
   return 0;
 }
 
+namespace {
+int log_posterior_impl(gpbt_chain_t ch, const double* X, double oob_value, double* lp, int* n_notpd, int64_t N,
+                       int path, void* stream, double* const* peers, int n_peers, int64_t peer_off);
+
+int scatter_result(const double* lp, double* const* peers, int n_peers, int64_t peer_off, int64_t N, cudaStream_t st) {
+  if (n_peers <= 0 || N <= 0) return 0;
+  PeerList pl;
+  pl.n = n_peers;
+  for (int r = 0; r < n_peers; r++) pl.p[r] = peers[r];
+  scatter_to_peers_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(lp, pl, peer_off, N);
+  LAUNCH_CHECK();
+  return 0;
+}
+}  // namespace
+
 extern "C" int gpbt_log_posterior(gpbt_chain_t ch, const double* X, double oob_value, double* lp, int* n_notpd,
                                   int64_t N, int path, void* stream) {
+  return log_posterior_impl(ch, X, oob_value, lp, n_notpd, N, path, stream, nullptr, 0, 0);
+}
+
+extern "C" int gpbt_log_posterior_scatter(gpbt_chain_t ch, const double* X, double oob_value, double* lp,
+                                          double* const* peers_host, int n_peers, int64_t peer_off, int* n_notpd,
+                                          int64_t N, int path, void* stream) {
+  if (n_peers < 0 || n_peers > kMaxPeers || (n_peers > 0 && !peers_host) || peer_off < 0)
+    return fail(GPBT_EINVAL, "gpbt_log_posterior_scatter: bad peer list");
+  return log_posterior_impl(ch, X, oob_value, lp, n_notpd, N, path, stream, peers_host, n_peers, peer_off);
+}
+
+namespace {
+int log_posterior_impl(gpbt_chain_t ch, const double* X, double oob_value, double* lp, int* n_notpd, int64_t N,
+                       int path, void* stream, double* const* peers, int n_peers, int64_t peer_off) {
   if (!ch || !X || !lp || N < 0) return fail(GPBT_EINVAL, "gpbt_log_posterior: bad argument");
   if (ch->device != current_device())
     return fail(GPBT_EINVAL, "chain lives on device %d, current device is %d", ch->device, current_device());
@@ -696,6 +738,8 @@ extern "C" int gpbt_log_posterior(gpbt_chain_t ch, const double* X, double oob_v
     prm.R = ch->R; prm.c0 = ch->c0; prm.lp = lp; prm.n_notpd = n_notpd; prm.s_perp = ch->s_perp;
     prm.logdetF_half = ch->logdetF_half; prm.oob_value = oob_value; prm.sys_const = kSysConst;
     prm.N = N; prm.p = ch->p; prm.Q = ch->Q;
+    prm.n_peers = n_peers; prm.peer_off = peer_off;
+    for (int r = 0; r < n_peers; r++) prm.peers[r] = peers[r];
     const unsigned grid = (unsigned)((N + kLrWarps - 1) / kLrWarps);
     if (ch->Q <= 32 && !getenv("GPBT_LOWRANK_GENERIC")) {
       switch ((ch->Q + 3) / 4) {
@@ -741,7 +785,7 @@ extern "C" int gpbt_log_posterior(gpbt_chain_t ch, const double* X, double oob_v
           lp + s, n_notpd);
       LAUNCH_CHECK();
     }
-    return 0;
+    return scatter_result(lp, peers, n_peers, peer_off, N, st);
   }
 
   // dense path: (a) -> (b) with the covariance materialised in HBM -> (c), in row chunks
@@ -759,8 +803,9 @@ extern "C" int gpbt_log_posterior(gpbt_chain_t ch, const double* X, double oob_v
                          kSysConst, nn, ch->M, st))
       return r;
   }
-  return 0;
+  return scatter_result(lp, peers, n_peers, peer_off, N, st);
 }
+}  // namespace
 
 extern "C" int gpbt_log_posterior_host(gpbt_chain_t ch, const double* X_host, double oob_value, double* lp_host,
                                        int* n_notpd_host, int64_t N, int path) {

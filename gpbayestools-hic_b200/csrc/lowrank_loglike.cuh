@@ -18,6 +18,8 @@
 
 namespace gpbt {
 
+constexpr int kMaxPeers = 16;
+
 struct LowrankParams {
   const double* __restrict__ X;       // [N, p]
   const double* __restrict__ lo;      // [p]
@@ -27,6 +29,11 @@ struct LowrankParams {
   const double* __restrict__ R;       // [Q, Q] upper triangular, row-major
   const double* __restrict__ c0;      // [Q]
   double* __restrict__ lp;            // [N]
+  // fused all-gather: when n_peers > 0 every result also goes to peers[r][peer_off + w] -- buffers of
+  // the other GPUs mapped into this process (NVLink peer stores), so no collective follows the kernel
+  double* peers[kMaxPeers];
+  int n_peers;
+  int64_t peer_off;
   int* __restrict__ n_notpd;          // may be null
   double s_perp, logdetF_half, oob_value, sys_const;
   int64_t N;
@@ -34,6 +41,11 @@ struct LowrankParams {
 };
 
 constexpr int kLrWarps = 4;
+
+__device__ __forceinline__ void lowrank_store(const LowrankParams& prm, int64_t w, double v) {
+  lowrank_store(prm, w, v);
+  for (int r = 0; r < prm.n_peers; r++) prm.peers[r][prm.peer_off + w] = v;
+}
 
 __host__ __device__ inline int lowrank_stride(int Q) { return Q | 1; }
 inline size_t lowrank_smem_bytes(int Q) {
@@ -74,7 +86,7 @@ __global__ void __launch_bounds__(kLrWarps * 32) lowrank_loglike_kernel(const Lo
     ok = ok && (x > prm.lo[d]) && (x < prm.hi[d]);
   }
   if (!__all_sync(0xffffffffu, ok)) {
-    if (lane == 0) prm.lp[w] = prm.oob_value;
+    if (lane == 0) lowrank_store(prm, w, prm.oob_value);
     return;
   }
 
@@ -123,7 +135,7 @@ __global__ void __launch_bounds__(kLrWarps * 32) lowrank_loglike_kernel(const Lo
   }
   if (!pd) {
     if (lane == 0) {
-      prm.lp[w] = prm.oob_value;
+      lowrank_store(prm, w, prm.oob_value);
       if (prm.n_notpd) atomicAdd(prm.n_notpd, 1);
     }
     return;
@@ -132,7 +144,7 @@ __global__ void __launch_bounds__(kLrWarps * 32) lowrank_loglike_kernel(const Lo
   for (int b = lane; b < Q; b += 32) logdet2 += log(dg[b]);
   logdet2 = warp_sum(logdet2);
   if (lane == 0)
-    prm.lp[w] = -0.5 * (prm.s_perp + quad) - 0.5 * logdet2 - prm.logdetF_half + prm.sys_const;
+    lowrank_store(prm, w, -0.5 * (prm.s_perp + quad) - 0.5 * logdet2 - prm.logdetF_half + prm.sys_const);
 }
 
 // ---- register-resident variant, Q <= 32 ----------------------------------------------------------
@@ -165,7 +177,7 @@ __global__ void __launch_bounds__(kLrWarps * 32) lowrank_loglike_reg_kernel(cons
     ok = ok && (x > prm.lo[d]) && (x < prm.hi[d]);
   }
   if (!__all_sync(0xffffffffu, ok)) {
-    if (lane == 0) prm.lp[w] = prm.oob_value;
+    if (lane == 0) lowrank_store(prm, w, prm.oob_value);
     return;
   }
   double* zs = zv[warp];
@@ -224,10 +236,10 @@ __global__ void __launch_bounds__(kLrWarps * 32) lowrank_loglike_reg_kernel(cons
   logdet2 = warp_sum(logdet2);
   if (lane == 0) {
     if (!pd) {
-      prm.lp[w] = prm.oob_value;
+      lowrank_store(prm, w, prm.oob_value);
       if (prm.n_notpd) atomicAdd(prm.n_notpd, 1);
     } else {
-      prm.lp[w] = -0.5 * (prm.s_perp + quad) - 0.5 * logdet2 - prm.logdetF_half + prm.sys_const;
+      lowrank_store(prm, w, -0.5 * (prm.s_perp + quad) - 0.5 * logdet2 - prm.logdetF_half + prm.sys_const);
     }
   }
 }

@@ -208,6 +208,19 @@ class DeviceChain:
             self._path(path), _stream_ptr(torch)))
         return lp_d
 
+    def log_target_scatter(self, X_d, oob_value, peer_ptrs, peer_off, lp_d=None, path=None):
+        """log_target_device with the all-gather fused in: each result is also stored to
+        peer_ptrs[r] + peer_off (device pointers of peer-mapped buffers).  No synchronisation."""
+        torch = _torch()
+        N = X_d.shape[0]
+        if lp_d is None:
+            lp_d = torch.empty(N, dtype=torch.float64, device=X_d.device)
+        arr = (C.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+        _lib.check(_lib.lib.gpbt_log_posterior_scatter(
+            self.handle(), X_d.data_ptr(), float(oob_value), lp_d.data_ptr(), C.cast(arr, C.c_void_p),
+            len(peer_ptrs), int(peer_off), None, N, self._path(path), _stream_ptr(torch)))
+        return lp_d
+
     def predict(self, X, extra_std=0.0, return_cov=True):
         """Chain._predict (src/mcmc.py:153-166): mean [N, M], block-diagonal cov [N, M, M]."""
         torch = _torch()

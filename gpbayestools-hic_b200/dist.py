@@ -20,6 +20,43 @@ def shard_bounds(N, world, rank):
     return lo, min(N, lo + per), per
 
 
+class PeerGather:
+    """All-gather of the per-walker results WITHOUT a collective call: every rank owns a symmetric
+    buffer that all other ranks of the box have mapped (torch symmetric memory: cuMem + NVLink peer
+    access); the last kernel of the log-posterior path stores each value straight into all of them
+    (gpbt_log_posterior_scatter) and one device-side barrier (~7 us) orders the ranks.  Two halves
+    alternate between calls so a fast rank never overwrites what a peer may still be reading.
+    Replaces an NCCL all-gather whose cost is pure latency (8 bytes per walker)."""
+
+    def __init__(self, rows_per_rank, device, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.rows = int(rows_per_rank)
+        self.buf = symm_mem.empty(2 * self.world * self.rows, dtype=torch.float64, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, self.group.group_name)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.parity = 0
+        self.buf.zero_()
+        self.hdl.barrier(channel=0)
+
+    def evaluate(self, chain, X_local, oob_value, path=None):
+        """chain: DeviceChain.  Returns the gathered vector [world * n_local] (a view of this rank's
+        symmetric buffer, valid until the call after next)."""
+        n = X_local.shape[0]
+        if n > self.rows:
+            raise ValueError("PeerGather was sized for %d rows per rank, got %d" % (self.rows, n))
+        half = self.parity * self.world * self.rows
+        self.parity ^= 1
+        peers = [p + 8 * half for p in self.ptrs]
+        chain.log_target_scatter(X_local, oob_value, peers, self.rank * n, path=path)
+        self.hdl.barrier(channel=0)
+        return self.buf[half:half + self.world * n]
+
+
 class ShardedEvaluator:
     def __init__(self, eval_fn, device, group=None):
         """eval_fn(X_local [n_local, p] tensor on `device`) -> lp_local [n_local] float64 tensor."""

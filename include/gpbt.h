@@ -148,6 +148,16 @@ int gpbt_chain_predict(gpbt_chain_t chain, const double* X_dev, double extra_std
 int gpbt_log_posterior(gpbt_chain_t chain, const double* X_dev, double oob_value, double* lp_dev,
                        int* n_notpd_dev, int64_t N, int path, void* stream);
 
+/* gpbt_log_posterior with the all-gather fused into the last kernel: every lp[w] is additionally
+ * stored to peers[r][peer_off + w], r < n_peers (<= 16), where peers[] are device pointers valid in
+ * this process -- buffers of the other GPUs mapped over NVLink (CUDA IPC / symmetric memory), or
+ * local ones.  peers_host is a HOST array of those pointers.  The caller orders the ranks (one
+ * barrier after the call) before anyone reads the gathered vector.  Replaces the NCCL all-gather of
+ * the per-walker log-posteriors, the only collective of the multi-GPU path.                       */
+int gpbt_log_posterior_scatter(gpbt_chain_t chain, const double* X_dev, double oob_value, double* lp_dev,
+                               double* const* peers_host, int n_peers, int64_t peer_off,
+                               int* n_notpd_dev, int64_t N, int path, void* stream);
+
 /* Same with HOST buffers: H2D of X, kernels, D2H of lp, one synchronisation.
  * This is the call behind Chain.log_posterior(X: np.ndarray) -> np.ndarray.                  */
 int gpbt_log_posterior_host(gpbt_chain_t chain, const double* X_host, double oob_value,

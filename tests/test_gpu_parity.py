@@ -361,3 +361,29 @@ def test_n1000_shape():
     assert np.max(np.abs(lp[rows][fin] - want[fin])) <= ABS_LP
     assert np.max(np.abs(ch.log_target(X[:64], -np.inf, path="dense") - lp[:64])[np.isfinite(lp[:64])]) <= ABS_LP
     ch.release()
+
+
+def test_scatter_to_peer_buffers():
+    """The fused all-gather store (gpbt_log_posterior_scatter) on one GPU: two local buffers stand in
+    for the peer-mapped ones; every path must deliver lp to both at the requested offset."""
+    import torch
+    from gpbt_b200.device import DeviceChain
+    g = goldens.load("c1_rbf")
+    states, _ = product_states(g)
+    ch = DeviceChain(states, g["lo"], g["hi"], g["y_exp"].reshape(-1), g["cov_exp"])
+    X_d = torch.from_numpy(np.ascontiguousarray(g["X"])).cuda()
+    N = X_d.shape[0]
+    want = ch.log_target_device(X_d, -np.inf)
+    for path in ("lowrank", "dense"):
+        bufs = [torch.full((3 * N,), 7.0, dtype=torch.float64, device="cuda") for _ in range(2)]
+        lp = ch.log_target_scatter(X_d, -np.inf, [b.data_ptr() for b in bufs], N, path=path)
+        torch.cuda.synchronize()
+        tol = 0.0 if path == "lowrank" else 1e-8
+        for b in bufs:
+            got = b[N:2 * N]
+            fin = torch.isfinite(want)
+            assert torch.equal(torch.isinf(got), torch.isinf(want))
+            assert float((got[fin] - want[fin]).abs().max()) <= tol
+            assert torch.all(b[:N] == 7.0) and torch.all(b[2 * N:] == 7.0)
+        assert torch.equal(lp, bufs[0][N:2 * N])
+    ch.release()
