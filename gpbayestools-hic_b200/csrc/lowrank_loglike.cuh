@@ -43,7 +43,7 @@ struct LowrankParams {
 constexpr int kLrWarps = 4;
 
 __device__ __forceinline__ void lowrank_store(const LowrankParams& prm, int64_t w, double v) {
-  lowrank_store(prm, w, v);
+  prm.lp[w] = v;
   for (int r = 0; r < prm.n_peers; r++) prm.peers[r][prm.peer_off + w] = v;
 }
 
