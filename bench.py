@@ -206,9 +206,13 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    saved_stdout = None
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
+        # NCCL prints a version banner on stdout when its first communicator is created (whatever
+        # NCCL_DEBUG says on this image): send everything but the final JSON line to stderr
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
 
     g, sts = load_c2()
@@ -393,8 +397,11 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     if line is not None:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
 
 
 def main():
