@@ -1,4 +1,5 @@
-"""Debug probe for PeerGather on 2+ GPUs."""
+"""PeerGather (fused all-gather over peer-mapped buffers) on 2+ GPUs, checked against an NCCL
+all-gather of the same values.  Launched by tests/test_multi_gpu.py under torchrun."""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -36,5 +37,15 @@ for path in ("dense", "lowrank"):
     dist.all_gather(gathered, want_local)
     ref = torch.cat(gathered)
     fin = torch.isfinite(ref)
-    print(rank, path, "gathered max diff", float((out[fin] - ref[fin]).abs().max()), flush=True)
+    err = float((out[fin] - ref[fin]).abs().max())
+    print(rank, path, "gathered max diff", err, flush=True)
+    assert err == 0.0 and torch.equal(torch.isinf(out), torch.isinf(ref)), (path, err)
+# several calls in a row: the two halves of the symmetric buffer alternate
+for i in range(5):
+    out = pg.evaluate(ch, X, -np.inf)
+    assert float((out[fin] - ref[fin]).abs().max()) == 0.0
+torch.cuda.synchronize()
+dist.barrier()
+if rank == 0:
+    print("PEER_GATHER_PASS", flush=True)
 dist.destroy_process_group()
