@@ -28,6 +28,7 @@ pg = PeerGather(N, dev)
 print(rank, "ptrs", [hex(p) for p in pg.ptrs], "buf", hex(pg.buf.data_ptr()), pg.buf.numel(), flush=True)
 # write through raw pointers with a trivial torch-free path first: our scatter kernel on the dense path
 for path in ("dense", "lowrank"):
+    want_local = ch.log_target_device(X, -np.inf, path=path)
     out = pg.evaluate(ch, X, -np.inf, path=path)
     torch.cuda.synchronize()
     mine = out[rank * N:(rank + 1) * N]
