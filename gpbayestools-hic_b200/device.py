@@ -180,6 +180,12 @@ class DeviceChain:
             _lib.lib.gpbt_chain_destroy(self._handle)
             self._handle = None
 
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass   # interpreter shutdown
+
     @staticmethod
     def _path(path):
         return {None: _lib.PATH_AUTO, "auto": _lib.PATH_AUTO, "dense": _lib.PATH_DENSE,

@@ -252,6 +252,12 @@ class EmulatorState:
             _lib.lib.gpbt_emulator_destroy(self._handle)
             self._handle = None
 
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass   # interpreter shutdown: the library may already be gone
+
     def __getstate__(self):
         d = dict(self.__dict__)
         d["_handle"] = None

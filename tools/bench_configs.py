@@ -61,6 +61,19 @@ for N in (1, 64, 128):
     emit({"config": "C1 (p5,n100,m50,q10)", "N_per_call": N, "evals_per_s": rate, "us_per_call": dt * 1e6,
           "max_abs_diff_vs_reference": float(np.max(np.abs(lp[fin] - g["lp_posterior"][:N][fin]))) if fin.any() else None,
           "note": "host API (Chain.log_posterior), one call per emcee half-step; bounded by launch + PCIe latency"})
+# a large ensemble on the small emulator (throughput of the n = 100 shape, device-timed)
+Xb = torch.from_numpy(np.ascontiguousarray(np.tile(g["X"], (512, 1)))).cuda()
+ch.log_target_device(Xb, -np.inf)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10):
+    ch.log_target_device(Xb, -np.inf)
+e1.record()
+torch.cuda.synchronize()
+emit({"config": "C1 (p5,n100,m50,q10)", "N_per_call": Xb.shape[0], "evals_per_s": Xb.shape[0] * 10 / (e0.elapsed_time(e1) * 1e-3),
+      "note": "device resident, large ensemble on the small emulator"})
+del Xb
 ch.release()
 
 # ---- config 2: p17 n500 m300 q20, pocoMC 4096 particles -----------------------------------------
