@@ -161,6 +161,8 @@ class DeviceChain:
         if lowrank and all(not (s.no_pca or s.exp_diag) for s in self.states) and self.Q <= self.M:
             self.lowrank = lowrank_factors(self.states, self.y_exp, self.cov_exp)
         self._handle = None
+        self._checked = self.lowrank is None
+        self.lowrank_check = None
 
     def handle(self):
         if self._handle is None:
@@ -174,6 +176,35 @@ class DeviceChain:
                 lr["s_perp"] if lr else 0.0, lr["logdetF_half"] if lr else 0.0))
             self._handle = h
         return self._handle
+
+    def _self_check(self, n_points=16, tol=1e-8):
+        """Once per chain: the exact low-rank path against the dense Cholesky path on a few points of
+        the box.  The identity is exact, but its host-side factors go through chol(F) and a QR; if F
+        (truncation + experimental covariance) is so ill-conditioned that the two paths drift apart,
+        the chain is rebuilt without the low-rank factors and every call takes the dense path."""
+        self._checked = True
+        rng = np.random.default_rng(20261018)
+        X = rng.uniform(self.lo, self.hi, (n_points, self.p))
+        a = self._call_host(X, -np.inf, _lib.PATH_LOWRANK)
+        b = self._call_host(X, -np.inf, _lib.PATH_DENSE)
+        ok = np.isfinite(a) & np.isfinite(b)
+        diff = float(np.max(np.abs(a[ok] - b[ok]))) if ok.any() else 0.0
+        self.lowrank_check = dict(points=int(ok.sum()), max_abs_diff=diff, tol=tol)
+        if not np.array_equal(np.isfinite(a), np.isfinite(b)) or diff > tol * max(1.0, float(np.max(np.abs(b[ok]), initial=0.0)) / 100.0):
+            import warnings
+            warnings.warn("gpbt_b200: low-rank and dense log-likelihood paths differ by %.2e on this chain "
+                          "(ill-conditioned truncation + experimental covariance?); using the dense path" % diff)
+            self.release()
+            self.lowrank = None
+
+    def _call_host(self, X, oob_value, path):
+        lp = np.empty(X.shape[0])
+        notpd = C.c_int(0)
+        _lib.check(_lib.lib.gpbt_log_posterior_host(
+            self.handle(), _lib.host_ptr(X), float(oob_value), _lib.host_ptr(lp), C.byref(notpd),
+            X.shape[0], path))
+        self.last_notpd = notpd.value
+        return lp
 
     def release(self):
         if self._handle is not None:
@@ -195,17 +226,15 @@ class DeviceChain:
         """Host buffers in/out through gpbt_log_posterior_host (H2D, kernels, D2H, one sync)."""
         _torch()
         X = as_rows(X, self.p)
-        lp = np.empty(X.shape[0])
-        notpd = C.c_int(0)
-        _lib.check(_lib.lib.gpbt_log_posterior_host(
-            self.handle(), _lib.host_ptr(X), float(oob_value), _lib.host_ptr(lp), C.byref(notpd),
-            X.shape[0], self._path(path)))
-        self.last_notpd = notpd.value
-        return lp
+        if not self._checked:
+            self._self_check()
+        return self._call_host(X, oob_value, self._path(path))
 
     def log_target_device(self, X_d, oob_value, lp_d=None, path=None):
         """Device tensors in/out on torch's current stream; no synchronisation."""
         torch = _torch()
+        if not self._checked:
+            self._self_check()
         N = X_d.shape[0]
         if lp_d is None:
             lp_d = torch.empty(N, dtype=torch.float64, device=X_d.device)
@@ -218,6 +247,8 @@ class DeviceChain:
         """log_target_device with the all-gather fused in: each result is also stored to
         peer_ptrs[r] + peer_off (device pointers of peer-mapped buffers).  No synchronisation."""
         torch = _torch()
+        if not self._checked:
+            self._self_check()
         N = X_d.shape[0]
         if lp_d is None:
             lp_d = torch.empty(N, dtype=torch.float64, device=X_d.device)

@@ -387,3 +387,26 @@ def test_scatter_to_peer_buffers():
             assert torch.all(b[:N] == 7.0) and torch.all(b[2 * N:] == 7.0)
         assert torch.equal(lp, bufs[0][N:2 * N])
     ch.release()
+
+
+def test_lowrank_self_check_falls_back():
+    """DeviceChain checks its low-rank factors against the dense path once; a chain whose fixed
+    covariance part is hopelessly ill-conditioned is switched to the dense path (with a warning) and
+    still returns the dense-path values."""
+    import warnings
+    from gpbt_b200.device import DeviceChain
+    g = goldens.load("odd_shape")
+    states, sts = product_states(g)
+    ok = DeviceChain(states, g["lo"], g["hi"], g["y_exp"].reshape(-1), g["cov_exp"])
+    ok.log_target(g["X"], -np.inf)
+    assert ok.lowrank is not None and ok.lowrank_check["max_abs_diff"] <= 1e-9
+    # sabotage the factors of a second chain: the self check must notice and fall back
+    bad = DeviceChain(states, g["lo"], g["hi"], g["y_exp"].reshape(-1), g["cov_exp"])
+    bad.lowrank["R"] = np.ascontiguousarray(bad.lowrank["R"] * (1.0 + 1e-3))
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        lp = bad.log_target(g["X"], -np.inf)
+    assert bad.lowrank is None and any("dense path" in str(w.message) for w in rec)
+    ref = g["lp_posterior"]
+    fin = np.isfinite(ref)
+    assert np.max(np.abs(lp[fin] - ref[fin])) <= ABS_LP
