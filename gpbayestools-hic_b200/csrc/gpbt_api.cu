@@ -125,7 +125,15 @@ struct gpbt_chain {
   int* notpd_dev = nullptr;
   cudaStream_t stream = nullptr;
   int64_t ws_bytes = 0;
+  // small-batch path: pinned host buffers mapped into the device address space (zero copy)
+  double *zc_x_host = nullptr, *zc_x_dev = nullptr;      // [kZeroCopyRows, p]
+  double *zc_lp_host = nullptr, *zc_lp_dev = nullptr;    // [kZeroCopyRows] + one slot holding the int counter
 };
+
+// Batches up to this many walkers skip the explicit H2D / D2H copies: X is read and lp is written
+// by the kernels directly in mapped pinned host memory (a few KB over PCIe), which removes three
+// cudaMemcpyAsync calls -- about 20 us of a 52 us call at N = 64.
+constexpr int64_t kZeroCopyRows = 512;
 
 extern "C" const char* gpbt_last_error(void) { return g_err.c_str(); }
 extern "C" int gpbt_version(void) { return 100; }
@@ -588,6 +596,8 @@ extern "C" int gpbt_chain_create(gpbt_chain_t* out, const gpbt_emulator_t* emus,
 
 extern "C" int gpbt_chain_destroy(gpbt_chain_t ch) {
   if (!ch) return 0;
+  if (ch->zc_x_host) cudaFreeHost(ch->zc_x_host);
+  if (ch->zc_lp_host) cudaFreeHost(ch->zc_lp_host);
   void* ptrs[] = {ch->lo, ch->hi, ch->y_exp, ch->cov_exp, ch->R, ch->c0, ch->z_mean, ch->z_var, ch->extra,
                   ch->mean, ch->cov, ch->x_dev, ch->lp_dev, ch->skip, ch->notpd_dev, ch->dmean, ch->dvar};
   for (void* p : ptrs)
@@ -812,8 +822,24 @@ extern "C" int gpbt_log_posterior_host(gpbt_chain_t ch, const double* X_host, do
   if (!ch || !X_host || !lp_host || N < 0) return fail(GPBT_EINVAL, "gpbt_log_posterior_host: bad argument");
   if (N == 0) return 0;
   CU(cudaSetDevice(ch->device));
-  if (int r = ensure_io(ch, N)) return r;
   cudaStream_t st = ch->stream;
+  if (N <= kZeroCopyRows && !getenv("GPBT_NO_ZEROCOPY")) {
+    if (!ch->zc_x_host) {
+      CU(cudaHostAlloc(&ch->zc_x_host, (size_t)kZeroCopyRows * ch->p * sizeof(double), cudaHostAllocMapped));
+      CU(cudaHostAlloc(&ch->zc_lp_host, (size_t)(kZeroCopyRows + 1) * sizeof(double), cudaHostAllocMapped));
+      CU(cudaHostGetDevicePointer(&ch->zc_x_dev, ch->zc_x_host, 0));
+      CU(cudaHostGetDevicePointer(&ch->zc_lp_dev, ch->zc_lp_host, 0));
+    }
+    memcpy(ch->zc_x_host, X_host, (size_t)N * ch->p * sizeof(double));
+    int* cnt_host = reinterpret_cast<int*>(ch->zc_lp_host + kZeroCopyRows);
+    int* cnt_dev = reinterpret_cast<int*>(ch->zc_lp_dev + kZeroCopyRows);
+    if (int r = gpbt_log_posterior(ch, ch->zc_x_dev, oob_value, ch->zc_lp_dev, cnt_dev, N, path, st)) return r;
+    CU(cudaStreamSynchronize(st));
+    memcpy(lp_host, ch->zc_lp_host, (size_t)N * sizeof(double));
+    if (n_notpd_host) *n_notpd_host = *cnt_host;
+    return 0;
+  }
+  if (int r = ensure_io(ch, N)) return r;
   CU(cudaMemcpyAsync(ch->x_dev, X_host, (size_t)N * ch->p * sizeof(double), cudaMemcpyHostToDevice, st));
   if (int r = gpbt_log_posterior(ch, ch->x_dev, oob_value, ch->lp_dev, ch->notpd_dev, N, path, st)) return r;
   CU(cudaMemcpyAsync(lp_host, ch->lp_dev, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, st));
