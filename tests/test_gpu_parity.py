@@ -410,3 +410,40 @@ def test_lowrank_self_check_falls_back():
     ref = g["lp_posterior"]
     fin = np.isfinite(ref)
     assert np.max(np.abs(lp[fin] - ref[fin])) <= ABS_LP
+
+
+def test_many_emulators_large_q():
+    """A chain of four emulators (Q = 40 > 32 PCs, M = 200 observables): the shared-memory low-rank
+    kernel takes over from the register one; values against the oracle and the dense path."""
+    from gpbt_b200.device import DeviceChain
+    g = goldens.load("c1_rbf")
+    states, sts = product_states(g)
+    k = 4
+    y_exp = np.tile(g["y_exp"].reshape(-1), k) * np.repeat(1.0 + 0.01 * np.arange(k), 50)
+    cov_exp = np.kron(np.eye(k), g["cov_exp"])
+    ch = DeviceChain(states * k, g["lo"], g["hi"], y_exp, cov_exp)
+    assert ch.Q == 40 and ch.M == 200 and ch.lowrank is not None
+    X = g["X"][:48]
+    lp = ch.log_target(X, -np.inf)
+    want = orc.log_posterior(sts * k, X, g["lo"], g["hi"], y_exp.reshape(1, -1), cov_exp)
+    fin = np.isfinite(want)
+    assert np.array_equal(np.isneginf(lp), ~fin)
+    assert np.max(np.abs(lp[fin] - want[fin])) <= ABS_LP
+    assert np.max(np.abs(ch.log_target(X, -np.inf, path="dense")[fin] - want[fin])) <= ABS_LP
+    ch.release()
+
+
+def test_long_batches_are_chunked_consistently():
+    """More rows than one internal chunk (32768 in the C layer): mean + diag(cov) of 70000 points
+    equals the same rows evaluated in small calls."""
+    import torch
+    from gpbt_b200.device import DeviceEmulator
+    g = goldens.load("c1_rbf")
+    states, _ = product_states(g)
+    de = DeviceEmulator(states[0])
+    rng = np.random.default_rng(5)
+    X = torch.from_numpy(rng.uniform(g["lo"], g["hi"], (70000, len(g["lo"])))).cuda()
+    mean, var = de.predict_diag_device(X)
+    for s in (0, 32760, 69990):
+        m2, v2 = de.predict_diag_device(X[s:s + 10].contiguous())
+        assert float((mean[s:s + 10] - m2).abs().max()) <= 1e-11 and float(((var[s:s + 10] - v2) / v2).abs().max()) <= 1e-10
