@@ -9,10 +9,13 @@
 // W_j = L_j^-1 (inverted once on the host in FP64): V^T = K W_j^T, so the O(N n^2) term is a
 // triangular GEMM that runs on the FP64 tensor pipe (DMMA.8x8x4).
 //
-// One CTA = one tile of TW walkers x one PC.
-//   phase 1  K^T[k][w] for k < n_pad into shared memory (FP64 pipe: distance + exp), z_mean on
-//            the fly.  Layout Kt[k*TW + (w ^ swz(k))] makes both the phase-1 stores and the
-//            phase-2 B-fragment loads bank-conflict free.
+// One CTA = one tile of TW walkers x one PC (TW = 16 with two CTAs resident per SM for large
+// batches, so one CTA's phase 1 overlaps the other's phase 2; 32 when two do not fit; 8 for small N).
+//   phase 1  the scaled design (rows X_train[k]/ell_j with alpha_j[k] appended) streams through
+//            shared memory in 128-row stages by TMA bulk copy (cp.async.bulk + mbarrier, double
+//            buffered); K^T[k][w] for k < n_pad goes to shared memory (FP64 pipe: distance + a
+//            branch-free exp), z_mean on the fly.  Layout Kt[k*TW + (w ^ swz(k))] makes both the
+//            phase-1 stores and the phase-2 B-fragment loads bank-conflict free.
 //   phase 2  for each 32-row block of W_j: acc[32 x TW] += W_j[rows, k] * Kt[k, :] over k <= row,
 //            A fragments straight from global/L2 (each element of W_j is needed by exactly one
 //            warp of the CTA, so staging it in shared memory buys nothing), then square and
