@@ -447,3 +447,53 @@ def test_long_batches_are_chunked_consistently():
     for s in (0, 32760, 69990):
         m2, v2 = de.predict_diag_device(X[s:s + 10].contiguous())
         assert float((mean[s:s + 10] - m2).abs().max()) <= 1e-11 and float(((var[s:s + 10] - v2) / v2).abs().max()) <= 1e-10
+
+
+RANDOM_SHAPES = [
+    # (p, n, m, q, kind)  -- odd / even / prime sizes, q = 1, q = m, tiny and mid-size designs
+    (1, 5, 3, 1, "RBF"), (2, 9, 4, 4, "Matern"), (3, 31, 7, 2, "RBF"), (4, 32, 8, 8, "Matern"),
+    (5, 33, 9, 3, "RBF"), (6, 63, 16, 5, "Matern"), (7, 64, 17, 6, "RBF"), (8, 65, 31, 9, "RBF"),
+    (9, 97, 33, 12, "Matern"), (11, 129, 20, 20, "RBF"), (13, 200, 81, 7, "RBF"), (24, 70, 12, 4, "Matern"),
+    (25, 50, 10, 3, "RBF"),   # p > 24: the generic (runtime parameter count) kernel
+]
+
+
+@pytest.mark.parametrize("shape", RANDOM_SHAPES, ids=lambda s: "p%d_n%d_m%d_q%d_%s" % s)
+def test_random_shapes_vs_oracle(shape):
+    """Shape fuzzing: emulator states of assorted sizes (synthetic data, fixed hyper-parameters) --
+    predict, every likelihood path and every walker-tile width against the oracle."""
+    import os
+    from gpbt_b200 import synthetic
+    from gpbt_b200.device import DeviceChain, DeviceEmulator
+    from gpbt_b200.state import EmulatorState
+    p, n, m, q, kind = shape
+    arr = synthetic.untrained_state_arrays(p, n, m, q, kind=kind, seed=p * 1000 + n)
+    st = EmulatorState.from_arrays(**arr, keep_L=True)
+    ost = st.oracle_dict()
+    lo, hi = synthetic.box(p)
+    rng = np.random.default_rng(n)
+    y_exp = synthetic.Simulator(p, m)(lo + 0.45 * (hi - lo))[0]
+    cov_exp = np.diag((0.05 * np.abs(y_exp)) ** 2)
+    N = int(rng.integers(1, 70))
+    X = synthetic.walkers(p, N, seed=m, frac_outside=0.1)
+    inside = np.all((X > lo) & (X < hi), axis=1)
+    ch = DeviceChain([st], lo, hi, y_exp, cov_exp)
+    want = orc.log_posterior([ost], X, lo, hi, y_exp.reshape(1, -1), cov_exp)
+    fin = np.isfinite(want)
+    scale = max(1.0, float(np.max(np.abs(want[fin]), initial=1.0)) / 100.0)
+    try:
+        for tile in ("8", "16", "32"):
+            os.environ["GPBT_PC_TILE"] = tile
+            for path in ("lowrank", "dense"):
+                lp = ch.log_target(X, -np.inf, path=path)
+                assert np.array_equal(np.isneginf(lp), ~fin), (shape, tile, path)
+                if fin.any():
+                    assert np.max(np.abs(lp[fin] - want[fin])) <= ABS_LP * scale, (shape, tile, path)
+    finally:
+        os.environ.pop("GPBT_PC_TILE", None)
+    if inside.any():
+        Xi = X[inside][:9]
+        mean, cov = DeviceEmulator(st).predict(Xi, return_cov=True, extra_std=0.03)
+        omean, ocov = orc.emulator_predict(ost, Xi, True, np.full(len(Xi), 0.03))
+        assert rel_err(mean, omean) <= REL and scaled_err(cov, ocov) <= REL, shape
+    ch.release()
