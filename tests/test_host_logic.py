@@ -1,6 +1,8 @@
 """CPU tests of the host-side logic that feeds the kernels: the exact low-rank factors
 (device.lowrank_factors) against the dense mvn_loglike of the oracle, state extraction from trained
 sklearn objects, the parameter-function curves, and pickling."""
+import os
+
 import numpy as np
 import pytest
 from hypothesis import given, settings
@@ -131,3 +133,63 @@ def test_golden_states_are_consistent():
     y = np.stack([s["L"][j] @ (s["L"][j].T @ s["alpha"][j]) for j in range(len(s["c"]))])
     assert np.all(np.abs(y.std(axis=1) - 1.0) < 0.05) and np.all(np.abs(y.mean(axis=1)) < 1e-8)
     assert states[0].device_bytes() > 0
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="the reference tree exists only in the build container")
+def test_state_extraction_from_a_reference_pickle(tmp_path):
+    """`Chain.loadEmulator` accepts dill pickles made by the REFERENCE's Emulator class: train one
+    with the unmodified reference, dill round trip, EmulatorState.from_trained, and the oracle on the
+    extracted state reproduces the reference's own predict / log_posterior."""
+    import subprocess
+    import sys
+    import textwrap
+    import gpbt_b200  # noqa: F401
+    from gpbt_b200 import synthetic
+    paths = synthetic.write_fixture(str(tmp_path), p=3, n=30, m=8)
+    # the reference is trained in a subprocess (its package is called `src`, and importing
+    # src.mcmc needs stub emcee / pocomc modules)
+    script = textwrap.dedent("""
+        import os, sys, types, dill, numpy as np
+        os.environ["WORKDIR"] = %r; os.environ["LOGLEVEL"] = "error"
+        sys.path.insert(0, "/root/reference")
+        em = types.ModuleType("emcee"); em.EnsembleSampler = type("EnsembleSampler", (), {"__init__": lambda s, *a, **k: None})
+        pm = types.ModuleType("pocomc"); pm.Prior = object; pm.Sampler = object
+        sys.modules["emcee"] = em; sys.modules["pocomc"] = pm
+        from src.emulator import Emulator
+        from src.mcmc import Chain
+        emu = Emulator(training_set_path=%r, parameter_file=%r, npc=3)
+        emu.trainEmulator([True] * emu.nev, kernel_type="Matern")
+        dill.dump(emu, open(%r, "wb"))
+        os.makedirs(os.path.join(%r, "mcmc"), exist_ok=True)
+        ch = Chain(mcmc_path=os.path.join(%r, "mcmc", "c.pkl"), expdata_path=%r, model_parafile=%r)
+        ch.loadEmulator([%r])
+        X = np.load(%r)
+        mean, cov = emu.predict(X, return_cov=True, extra_std=np.zeros(len(X)))
+        np.savez(%r, mean=mean, cov=cov, lp=ch.log_posterior(X), y=ch.expdata, c=ch.expdata_cov, lo=ch.min, hi=ch.max)
+    """) % (str(tmp_path), paths["train"], paths["par"], str(tmp_path / "ref_emu.pkl"), str(tmp_path), str(tmp_path),
+            paths["exp"], paths["par"], str(tmp_path / "ref_emu.pkl"), str(tmp_path / "X.npy"), str(tmp_path / "ref_out.npz"))
+    X = synthetic.walkers(3, 25, seed=2)
+    np.save(tmp_path / "X.npy", X)
+    res = subprocess.run([sys.executable, "-W", "ignore", "-c", script], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-3000:]
+    ref = np.load(tmp_path / "ref_out.npz")
+    # unpickling needs the reference's package on the path, exactly as in a user's environment
+    import dill
+    sys.path.insert(0, "/root/reference")
+    try:
+        with open(tmp_path / "ref_emu.pkl", "rb") as fh:
+            emu = dill.load(fh)
+    finally:
+        sys.path.remove("/root/reference")
+        for name in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
+            del sys.modules[name]
+    from gpbt_b200.state import EmulatorState
+    stt = EmulatorState.from_trained(emu, keep_L=True)
+    assert stt.kind == "Matern" and (stt.p, stt.n, stt.q, stt.m) == (3, 30, 3, 8)
+    od = stt.oracle_dict()
+    mean, cov = orc.emulator_predict(od, X, True, np.zeros(len(X)))
+    assert np.max(np.abs(mean - ref["mean"]) / np.abs(ref["mean"])) <= 1e-9
+    assert np.max(np.abs(cov - ref["cov"])) <= 1e-9 * np.max(np.abs(ref["cov"]))
+    lp = orc.log_posterior([od], X, ref["lo"], ref["hi"], ref["y"], ref["c"])
+    fin = np.isfinite(ref["lp"])
+    assert np.array_equal(np.isfinite(lp), fin) and np.max(np.abs(lp[fin] - ref["lp"][fin])) <= 1e-8
