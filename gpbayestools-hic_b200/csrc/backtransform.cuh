@@ -80,31 +80,36 @@ __global__ void __launch_bounds__(128) backtransform_mean_kernel(const Backtrans
 }
 
 // ---- dense covariance (PCA mode) on the FP64 tensor pipe --------------------------------------
-// Persistent CTAs (4 warps) keep A in shared memory and walk over (walker, 32-row tile) work items.
-// For an item, D[i][j] = Ctrunc[i][j] + sum_k (v_k A[k][i]) * A[k][j]: the accumulators are
-// initialised with the Ctrunc tile (its L2 latency overlaps the other warps' tensor work), the
-// A-operand fragment (row i = g, k = t) and the B-operand fragment (k = t, col j = g) both come from
-// the same [q_pad][m_ld] array (m_ld = 4 mod 8 keeps those loads bank-conflict free).
-// cov is symmetric, so an item only computes the column blocks at or right of its diagonal tile and
-// stores every off-diagonal 8x8 block twice: directly (16-byte stores, 64-byte row segments per
-// quad) and mirrored (lanes of equal t write 8 consecutive doubles of a row).  That halves the
+// D[i][j] = Ctrunc[i][j] + sum_k (v_k A[k][i]) * A[k][j] per walker.  Persistent CTAs keep A in
+// shared memory ([q_pad][m_ld], m_ld = 4 mod 8: the A-operand fragment (row i = g, k = t) and the
+// B-operand fragment (k = t, col j = g) are both read from it without bank conflicts); their WARPS
+// walk independently over work items (walker, 32-row tile rt, group of four n8 column blocks), so
+// there is no block-level synchronisation after the prologue.  The accumulators start from the
+// Ctrunc tile (its L2 latency overlaps other warps' tensor work); v_k multiplies the A fragment in
+// registers.
+// cov is symmetric, so only the column groups at or right of the diagonal 32x32 tile are computed
+// and every off-diagonal 8x8 block is stored twice: directly (16-byte stores, 64-byte row segments
+// per quad) and mirrored (lanes of equal t write 8 consecutive doubles of a row).  That halves the
 // tensor work, which otherwise is as large as the HBM write stream (both ~30 k cycles per walker
-// per SM at q = 20, m = 300).  The n8 column blocks of an item are dealt to the 4 warps as
-// contiguous ranges; the grid size is chosen coprime to the number of row tiles so that the
-// round-robin hands every CTA all tile sizes.
+// per SM at q = 20, m = 300).
 constexpr int kBtThreads = 128;
 constexpr int kBtWarps = kBtThreads / 32;
 constexpr int kBtRows = 32;
 
-inline size_t backtransform_smem_bytes(int q_pad, int m_ld) {
-  return sizeof(double) * ((size_t)q_pad * m_ld + 2 * (size_t)q_pad * kBtRows);
+inline size_t backtransform_smem_bytes(int q_pad, int m_ld) { return sizeof(double) * (size_t)q_pad * m_ld; }
+
+// number of (row tile, column group) items of one walker and the decoding of an item index
+__host__ __device__ inline int bt_items_per_walker(int m) {
+  const int n_rt = (m + kBtRows - 1) / kBtRows, n_nb = (m + 7) / 8;
+  int cnt = 0;
+  for (int rt = 0; rt < n_rt; rt++) cnt += (n_nb - 4 * rt + 3) / 4;
+  return cnt;
 }
 
-__global__ void __launch_bounds__(kBtThreads, 3) backtransform_cov_kernel(const BacktransformParams prm, int q_pad) {
+__global__ void __launch_bounds__(kBtThreads, 4) backtransform_cov_kernel(const BacktransformParams prm, int q_pad) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int m = prm.m, m_ld = prm.m_ld;
   double* As = reinterpret_cast<double*>(smem_raw);  // [q_pad][m_ld]
-  double* Av = As + (size_t)q_pad * m_ld;            // [2][q_pad][32]: v_k * A[k][i0 + r], double buffered
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
 
@@ -114,93 +119,94 @@ __global__ void __launch_bounds__(kBtThreads, 3) backtransform_cov_kernel(const 
   }
   __syncthreads();
 
-  const int n_rt = (m + kBtRows - 1) / kBtRows;
-  const int64_t n_items = prm.N * n_rt;
+  const int n_rt = (m + kBtRows - 1) / kBtRows, n_nb = (m + 7) / 8;
+  const int per_walker = bt_items_per_walker(m);
+  const int64_t n_items = prm.N * per_walker;
   const int64_t ldc = prm.ld_cov, off = prm.col_off;
   const bool vec_ok = (ldc % 2 == 0) && (off % 2 == 0) && ((reinterpret_cast<uintptr_t>(prm.cov) & 15) == 0);
   const bool ct_vec = (m % 2 == 0) && ((reinterpret_cast<uintptr_t>(prm.Ctrunc) & 15) == 0);
-  const int n_nb = (m + 7) / 8;
+  const int64_t warp_stride = (int64_t)gridDim.x * kBtWarps;
 
-  int buf = 0;
-  for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x, buf ^= 1) {
-    const int64_t w = item / n_rt;
-    const int rt = (int)(item - w * n_rt);
-    const int i0 = rt * kBtRows;
-    double* av = Av + (size_t)buf * q_pad * kBtRows;
-    for (int idx = tid; idx < q_pad * kBtRows; idx += kBtThreads) {
-      const int k = idx / kBtRows, r = idx - k * kBtRows;
-      const double v = k < prm.q ? prm.z_var[w * prm.ldz + k] : 0.0;
-      av[idx] = (i0 + r < m) ? v * As[(size_t)k * m_ld + i0 + r] : 0.0;
+  for (int64_t item = (int64_t)blockIdx.x * kBtWarps + warp; item < n_items; item += warp_stride) {
+    const int64_t w = item / per_walker;
+    int rem = (int)(item - w * per_walker);
+    int rt = 0;
+    for (;; rt++) {  // items of a walker are ordered by row tile, then column group
+      const int cnt = (n_nb - 4 * rt + 3) / 4;
+      if (rem < cnt) break;
+      rem -= cnt;
     }
-    __syncthreads();  // (double buffered: the previous item's readers of the other buffer are done)
+    const int i0 = rt * kBtRows, nb_first = 4 * rt, nb0 = nb_first + 4 * rem;
+    const int nb_hi = min(nb0 + 4, n_nb);
     double* wbase = prm.cov + (size_t)w * ldc * ldc + (size_t)off * ldc + off;  // block (0,0) of this emulator
-    // column blocks 4*rt .. n_nb-1 of this item over the 4 warps
-    const int nb_first = 4 * rt, nb_cnt = n_nb - nb_first;
-    const int nb_per = (nb_cnt + kBtWarps - 1) / kBtWarps;
-    const int nb_lo = min(nb_first + warp * nb_per, n_nb), nb_hi = min(nb_lo + nb_per, n_nb);
-    for (int nb0 = nb_lo; nb0 < nb_hi; nb0 += 4) {
-      double acc[4][4][2];
-      // accumulators start from the Ctrunc tile; lane owns D[8mb + g][8nb + 2t + {0,1}]
+    const double* zv = prm.z_var + w * prm.ldz;
+
+    double acc[4][4][2];
+    // accumulators start from the Ctrunc tile; lane owns D[8mb + g][8nb + 2t + {0,1}]
 #pragma unroll
-      for (int mb = 0; mb < 4; mb++) {
-        const int i = i0 + 8 * mb + g;
+    for (int mb = 0; mb < 4; mb++) {
+      const int i = i0 + 8 * mb + g;
 #pragma unroll
-        for (int nb = 0; nb < 4; nb++) {
-          const int j = 8 * (nb0 + nb) + 2 * t;
-          const bool in = (i < m) && (nb0 + nb < nb_hi);
-          if (in && ct_vec && j + 1 < m) {
-            const double2 c2 = ldg2(prm.Ctrunc + (size_t)i * m + j);
-            acc[mb][nb][0] = c2.x;
-            acc[mb][nb][1] = c2.y;
-          } else {
-            acc[mb][nb][0] = (in && j < m) ? __ldg(prm.Ctrunc + (size_t)i * m + j) : 0.0;
-            acc[mb][nb][1] = (in && j + 1 < m) ? __ldg(prm.Ctrunc + (size_t)i * m + j + 1) : 0.0;
-          }
-        }
-      }
-      for (int k0 = 0; k0 < q_pad; k0 += 4) {
-        double a[4], b[4];
-#pragma unroll
-        for (int mb = 0; mb < 4; mb++) a[mb] = av[(k0 + t) * kBtRows + 8 * mb + g];
-#pragma unroll
-        for (int nb = 0; nb < 4; nb++) {
-          const int j = 8 * (nb0 + nb) + g;
-          b[nb] = j < m_ld ? As[(size_t)(k0 + t) * m_ld + j] : 0.0;
-        }
-#pragma unroll
-        for (int nb = 0; nb < 4; nb++)
-          if (nb0 + nb < nb_hi) {
-#pragma unroll
-            for (int mb = 0; mb < 4; mb++) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
-          }
-      }
-#pragma unroll
-      for (int mb = 0; mb < 4; mb++) {
-        const int i = i0 + 8 * mb + g;
-        if (i >= m) continue;
-#pragma unroll
-        for (int nb = 0; nb < 4; nb++) {
-          const int j = 8 * (nb0 + nb) + 2 * t;
-          if (nb0 + nb >= nb_hi || j >= m) continue;
-          double* row = wbase + (size_t)i * ldc;
-          if (vec_ok && j + 1 < m) {
-            *reinterpret_cast<double2*>(row + j) = make_double2(acc[mb][nb][0], acc[mb][nb][1]);
-          } else {
-            row[j] = acc[mb][nb][0];
-            if (j + 1 < m) row[j + 1] = acc[mb][nb][1];
-          }
-          // mirror of the blocks right of the diagonal 32x32 tile: cov[j][i] = cov[i][j]
-          if (nb0 + nb >= nb_first + 4) {
-            wbase[(size_t)j * ldc + i] = acc[mb][nb][0];
-            if (j + 1 < m) wbase[(size_t)(j + 1) * ldc + i] = acc[mb][nb][1];
-          }
+      for (int nb = 0; nb < 4; nb++) {
+        const int j = 8 * (nb0 + nb) + 2 * t;
+        const bool in = (i < m) && (nb0 + nb < nb_hi);
+        if (in && ct_vec && j + 1 < m) {
+          const double2 c2 = ldg2(prm.Ctrunc + (size_t)i * m + j);
+          acc[mb][nb][0] = c2.x;
+          acc[mb][nb][1] = c2.y;
+        } else {
+          acc[mb][nb][0] = (in && j < m) ? __ldg(prm.Ctrunc + (size_t)i * m + j) : 0.0;
+          acc[mb][nb][1] = (in && j + 1 < m) ? __ldg(prm.Ctrunc + (size_t)i * m + j + 1) : 0.0;
         }
       }
     }
-    // zero the parts of these rows that lie outside the diagonal block (multi-emulator chains)
-    if (ldc > m) {
+    for (int k0 = 0; k0 < q_pad; k0 += 4) {
+      const double vk = (k0 + t < prm.q) ? zv[k0 + t] : 0.0;
+      double a[4], b[4];
+#pragma unroll
+      for (int mb = 0; mb < 4; mb++) {
+        const int i = i0 + 8 * mb + g;
+        a[mb] = (i < m_ld) ? vk * As[(size_t)(k0 + t) * m_ld + i] : 0.0;
+      }
+#pragma unroll
+      for (int nb = 0; nb < 4; nb++) {
+        const int j = 8 * (nb0 + nb) + g;
+        b[nb] = j < m_ld ? As[(size_t)(k0 + t) * m_ld + j] : 0.0;
+      }
+#pragma unroll
+      for (int nb = 0; nb < 4; nb++)
+        if (nb0 + nb < nb_hi) {
+#pragma unroll
+          for (int mb = 0; mb < 4; mb++) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
+        }
+    }
+#pragma unroll
+    for (int mb = 0; mb < 4; mb++) {
+      const int i = i0 + 8 * mb + g;
+      if (i >= m) continue;
+#pragma unroll
+      for (int nb = 0; nb < 4; nb++) {
+        const int j = 8 * (nb0 + nb) + 2 * t;
+        if (nb0 + nb >= nb_hi || j >= m) continue;
+        double* row = wbase + (size_t)i * ldc;
+        if (vec_ok && j + 1 < m) {
+          *reinterpret_cast<double2*>(row + j) = make_double2(acc[mb][nb][0], acc[mb][nb][1]);
+        } else {
+          row[j] = acc[mb][nb][0];
+          if (j + 1 < m) row[j + 1] = acc[mb][nb][1];
+        }
+        // mirror of the blocks right of the diagonal 32x32 tile: cov[j][i] = cov[i][j]
+        if (nb0 + nb >= nb_first + 4) {
+          wbase[(size_t)j * ldc + i] = acc[mb][nb][0];
+          if (j + 1 < m) wbase[(size_t)(j + 1) * ldc + i] = acc[mb][nb][1];
+        }
+      }
+    }
+    // zero the parts of these rows that lie outside the diagonal block (multi-emulator chains);
+    // done by the item that owns the diagonal tile of the row tile
+    if (ldc > m && rem == 0) {
       double* rows0 = prm.cov + ((size_t)w * ldc + off + i0) * ldc;
-      for (int r = warp; r < kBtRows && i0 + r < m; r += kBtWarps)
+      for (int r = 0; r < kBtRows && i0 + r < m; r++)
         for (int64_t cidx = lane; cidx < ldc; cidx += 32)
           if (cidx < off || cidx >= off + m) rows0[(size_t)r * ldc + cidx] = 0.0;
     }

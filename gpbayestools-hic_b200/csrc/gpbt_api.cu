@@ -357,16 +357,10 @@ int run_backtransform(gpbt_emulator_t e, const double* zm, const double* zv, int
     if (smem > (size_t)max_optin_smem())
       return fail(GPBT_ESHAPE, "backtransform: q*m = %d*%d does not fit in shared memory", e->q, e->m);
     if (int r = ensure_dynamic_smem<backtransform_cov_kernel>(smem)) return r;
-    const int64_t items = N * ((e->m + kBtRows - 1) / kBtRows);
-    int per_sm = (int)std::min<size_t>(3, (228 * 1024 - 4096) / (smem + 1024));
+    const int64_t items = N * bt_items_per_walker(e->m);      // one per warp
+    int per_sm = (int)std::min<size_t>(4, (228 * 1024 - 4096) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
-    // persistent grid, coprime to the number of row tiles: the round-robin then hands every CTA
-    // all tile sizes of the triangular work
-    const int n_rt = (e->m + kBtRows - 1) / kBtRows;
-    int64_t gsz = std::min<int64_t>(items, (int64_t)148 * per_sm);
-    auto gcd = [](int64_t a, int64_t b) { while (b) { const int64_t r = a % b; a = b; b = r; } return a; };
-    while (gsz > 1 && gcd(gsz, n_rt) != 1) gsz--;
-    const unsigned grid = (unsigned)gsz;
+    const unsigned grid = (unsigned)std::min<int64_t>((items + kBtWarps - 1) / kBtWarps, (int64_t)148 * per_sm);
     backtransform_cov_kernel<<<grid, kBtThreads, smem, st>>>(prm, e->q_pad);
     LAUNCH_CHECK();
   }
