@@ -323,6 +323,13 @@ def run_ours(args):
             traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         except (OSError, KeyError, ValueError):
             pass
+        # HBM denominator: the driver's measured copy rate, else the profiling guide's fallback
+        hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                hbm_peak, hbm_src = float(json.load(fh)["hbm_gbs"]), "MEASURED_PEAKS.json"
+        except (OSError, KeyError, ValueError):
+            pass
         # FP64 roofline denominator: cuBLAS DGEMM, measured here
         n = 8192 if args.dgemm else 0
         peak, peak_src = 35.45, "profiles/r01_dgemm_peak.json (cuBLAS DGEMM 8192^3 on this pool)"
@@ -388,6 +395,8 @@ def run_ours(args):
                                          "algorithmic HBM bytes are 8p in + 16q out = 456 B per evaluation (1.9 MB per launch): "
                                          "the rest is the 21 MB lower triangle of L^-1 streamed once into L2",
                          "hbm_achieved_GBps": (traffic or 0) / (ka_ms * 1e-3) / 1e9,
+                         "hbm_peak_GBps": hbm_peak, "hbm_peak_source": hbm_src,
+                         "hbm_frac": (traffic or 0) / (ka_ms * 1e-3) / 1e9 / hbm_peak,
                          "peak_source": peak_src, "ms_per_launch": ka_ms,
                          "algorithmic_flops_per_eval": flops_pc_predict(SHAPE["p"], SHAPE["n"], SHAPE["q"]),
                          "dtype": "FP64 DMMA.8x8x4 + DFMA (one shared pipe, 37.1 TFLOP/s DMMA issue peak measured)"},
