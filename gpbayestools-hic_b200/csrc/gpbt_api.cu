@@ -114,6 +114,8 @@ struct gpbt_chain {
   std::vector<int> q_off, m_off;
   int p, Q, M, device;
   bool has_lowrank, has_diag;
+  bool lr_separable = false;          // R is block diagonal over the emulators
+  std::vector<double*> R_blocks;      // per-emulator q_e x q_e copies of the diagonal blocks of R
   double s_perp, logdetF_half;
   double *lo, *hi, *y_exp, *cov_exp, *R, *c0;
   // workspaces (grown on demand)
@@ -581,6 +583,27 @@ extern "C" int gpbt_chain_create(gpbt_chain_t* out, const gpbt_emulator_t* emus,
   if (R) {
     h.assign(R, R + (size_t)ch->Q * ch->Q); if (int r = upload(&ch->R, h)) return r;
     h.assign(c0, c0 + ch->Q); if (int r = upload(&ch->c0, h)) return r;
+    // block diagonal over the emulators?  (exact zeros: the host builds R per block in that case)
+    bool sep = n_emu > 1;
+    for (int a = 0; a < ch->Q && sep; a++)
+      for (int b2 = 0; b2 < ch->Q; b2++) {
+        int ea = 0, eb = 0;
+        while (ea + 1 < n_emu && a >= ch->q_off[ea + 1]) ea++;
+        while (eb + 1 < n_emu && b2 >= ch->q_off[eb + 1]) eb++;
+        if (ea != eb && R[(size_t)a * ch->Q + b2] != 0.0) { sep = false; break; }
+      }
+    ch->lr_separable = sep;
+    if (sep) {
+      for (int e = 0; e < n_emu; e++) {
+        const int q0 = ch->q_off[e], qe = emus[e]->q;
+        h.assign((size_t)qe * qe, 0.0);
+        for (int a = 0; a < qe; a++)
+          for (int b2 = 0; b2 < qe; b2++) h[(size_t)a * qe + b2] = R[(size_t)(q0 + a) * ch->Q + q0 + b2];
+        double* d = nullptr;
+        if (int r = upload(&d, h)) return r;
+        ch->R_blocks.push_back(d);
+      }
+    }
   }
   CU(cudaMalloc(&ch->notpd_dev, sizeof(int)));
   CU(cudaStreamCreateWithFlags(&ch->stream, cudaStreamNonBlocking));
@@ -590,6 +613,7 @@ extern "C" int gpbt_chain_create(gpbt_chain_t* out, const gpbt_emulator_t* emus,
 
 extern "C" int gpbt_chain_destroy(gpbt_chain_t ch) {
   if (!ch) return 0;
+  for (double* d : ch->R_blocks) cudaFree(d);
   if (ch->zc_x_host) cudaFreeHost(ch->zc_x_host);
   if (ch->zc_lp_host) cudaFreeHost(ch->zc_lp_host);
   void* ptrs[] = {ch->lo, ch->hi, ch->y_exp, ch->cov_exp, ch->R, ch->c0, ch->z_mean, ch->z_var, ch->extra,
@@ -737,28 +761,41 @@ int log_posterior_impl(gpbt_chain_t ch, const double* X, double oob_value, doubl
       if (int r = run_pc_predict(ch->emus[e], X, nullptr, ch->z_mean + ch->q_off[e], ch->z_var + ch->q_off[e],
                                  ch->Q, N, st))
         return r;
-    LowrankParams prm;
-    prm.X = X; prm.lo = ch->lo; prm.hi = ch->hi; prm.z_mean = ch->z_mean; prm.z_var = ch->z_var;
-    prm.R = ch->R; prm.c0 = ch->c0; prm.lp = lp; prm.n_notpd = n_notpd; prm.s_perp = ch->s_perp;
-    prm.logdetF_half = ch->logdetF_half; prm.oob_value = oob_value; prm.sys_const = kSysConst;
-    prm.N = N; prm.p = ch->p; prm.Q = ch->Q;
-    prm.n_peers = n_peers; prm.peer_off = peer_off;
-    for (int r = 0; r < n_peers; r++) prm.peers[r] = peers[r];
-    const unsigned grid = (unsigned)((N + kLrWarps - 1) / kLrWarps);
-    if (ch->Q <= 32 && !getenv("GPBT_LOWRANK_GENERIC")) {
-      switch ((ch->Q + 3) / 4) {
+    // One launch over all Q PCs, or -- when R is block diagonal over the emulators (the experimental
+    // covariance does not couple them) -- one launch per emulator block: log L is then a sum of
+    // per-block terms, every block fits the register kernel (q_e <= 32) and the cubic cost is in q_e.
+    const int n_blocks = ch->lr_separable ? (int)ch->emus.size() : 1;
+    for (int blk = 0; blk < n_blocks; blk++) {
+      const int q0 = ch->lr_separable ? ch->q_off[blk] : 0;
+      const int qb = ch->lr_separable ? ch->emus[blk]->q : ch->Q;
+      LowrankParams prm;
+      prm.X = X; prm.lo = ch->lo; prm.hi = ch->hi; prm.z_mean = ch->z_mean; prm.z_var = ch->z_var;
+      prm.ldz = ch->Q; prm.z_off = q0; prm.accumulate = blk > 0;
+      prm.R = ch->lr_separable ? ch->R_blocks[blk] : ch->R; prm.c0 = ch->c0 + q0; prm.lp = lp; prm.n_notpd = n_notpd;
+      // the walker-independent constants enter once, with the first block
+      prm.s_perp = blk == 0 ? ch->s_perp : 0.0;
+      prm.logdetF_half = blk == 0 ? ch->logdetF_half : 0.0;
+      prm.oob_value = oob_value; prm.sys_const = blk == 0 ? kSysConst : 0.0;
+      prm.N = N; prm.p = ch->p; prm.Q = qb;
+      // peers receive the running value of every block; the last launch leaves the final one
+      prm.n_peers = n_peers; prm.peer_off = peer_off;
+      for (int r = 0; r < n_peers; r++) prm.peers[r] = peers[r];
+      const unsigned grid = (unsigned)((N + kLrWarps - 1) / kLrWarps);
+      if (qb <= 32 && !getenv("GPBT_LOWRANK_GENERIC")) {
+        switch ((qb + 3) / 4) {
 #define GPBT_Q(QP) case QP / 4: lowrank_loglike_reg_kernel<QP><<<grid, kLrWarps * 32, 0, st>>>(prm); break;
-        GPBT_Q(4) GPBT_Q(8) GPBT_Q(12) GPBT_Q(16) GPBT_Q(20) GPBT_Q(24) GPBT_Q(28) GPBT_Q(32)
+          GPBT_Q(4) GPBT_Q(8) GPBT_Q(12) GPBT_Q(16) GPBT_Q(20) GPBT_Q(24) GPBT_Q(28) GPBT_Q(32)
 #undef GPBT_Q
+        }
+        LAUNCH_CHECK();
+        continue;
       }
+      const size_t smem = lowrank_smem_bytes(qb);
+      if (smem > (size_t)max_optin_smem()) return fail(GPBT_ESHAPE, "low-rank path: Q = %d too large", qb);
+      if (int r = ensure_dynamic_smem<lowrank_loglike_kernel>(smem)) return r;
+      lowrank_loglike_kernel<<<grid, kLrWarps * 32, smem, st>>>(prm);
       LAUNCH_CHECK();
-      return 0;
     }
-    const size_t smem = lowrank_smem_bytes(ch->Q);
-    if (smem > (size_t)max_optin_smem()) return fail(GPBT_ESHAPE, "low-rank path: Q = %d too large", ch->Q);
-    if (int r = ensure_dynamic_smem<lowrank_loglike_kernel>(smem)) return r;
-    lowrank_loglike_kernel<<<grid, kLrWarps * 32, smem, st>>>(prm);
-    LAUNCH_CHECK();
     return 0;
   }
 

@@ -24,8 +24,14 @@ struct LowrankParams {
   const double* __restrict__ X;       // [N, p]
   const double* __restrict__ lo;      // [p]
   const double* __restrict__ hi;      // [p]
-  const double* __restrict__ z_mean;  // [N, Q]
-  const double* __restrict__ z_var;   // [N, Q]
+  const double* __restrict__ z_mean;  // [N, ldz], this block's PCs start at column z_off
+  const double* __restrict__ z_var;   // [N, ldz]
+  int64_t ldz;
+  int z_off;
+  // Block-separable chains (experimental covariance block diagonal over the emulators): log L is a
+  // sum over emulator blocks, evaluated by one launch per block; all but the first ADD their term to
+  // lp (and to the peer buffers) instead of storing it.
+  int accumulate;
   const double* __restrict__ R;       // [Q, Q] upper triangular, row-major
   const double* __restrict__ c0;      // [Q]
   double* __restrict__ lp;            // [N]
@@ -42,7 +48,16 @@ struct LowrankParams {
 
 constexpr int kLrWarps = 4;
 
-__device__ __forceinline__ void lowrank_store(const LowrankParams& prm, int64_t w, double v) {
+// `term` is this block's contribution; `failed` (out of bounds / not positive definite) forces the
+// out-of-bounds value whatever the other blocks say
+__device__ __forceinline__ void lowrank_store(const LowrankParams& prm, int64_t w, double term, bool failed = false) {
+  double v = term;
+  if (failed) {
+    v = prm.oob_value;
+  } else if (prm.accumulate) {
+    const double prev = prm.lp[w];
+    v = (prev == prm.oob_value) ? prev : prev + term;   // an earlier block already failed this walker
+  }
   prm.lp[w] = v;
   for (int r = 0; r < prm.n_peers; r++) prm.peers[r][prm.peer_off + w] = v;
 }
@@ -86,13 +101,13 @@ __global__ void __launch_bounds__(kLrWarps * 32) lowrank_loglike_kernel(const Lo
     ok = ok && (x > prm.lo[d]) && (x < prm.hi[d]);
   }
   if (!__all_sync(0xffffffffu, ok)) {
-    if (lane == 0) lowrank_store(prm, w, prm.oob_value);
+    if (lane == 0) lowrank_store(prm, w, 0.0, true);
     return;
   }
 
   for (int a = lane; a < Q; a += 32) {
-    zs[a] = prm.z_mean[w * Q + a];
-    vs[a] = prm.z_var[w * Q + a];
+    zs[a] = prm.z_mean[w * prm.ldz + prm.z_off + a];
+    vs[a] = prm.z_var[w * prm.ldz + prm.z_off + a];
   }
   __syncwarp();
   // c = c0 + R z ;  S[:, b] (rows a >= b) = delta_ab + sum_k R[a][k] v_k R[b][k]
@@ -135,7 +150,7 @@ __global__ void __launch_bounds__(kLrWarps * 32) lowrank_loglike_kernel(const Lo
   }
   if (!pd) {
     if (lane == 0) {
-      lowrank_store(prm, w, prm.oob_value);
+      lowrank_store(prm, w, 0.0, true);
       if (prm.n_notpd) atomicAdd(prm.n_notpd, 1);
     }
     return;
@@ -177,14 +192,14 @@ __global__ void __launch_bounds__(kLrWarps * 32) lowrank_loglike_reg_kernel(cons
     ok = ok && (x > prm.lo[d]) && (x < prm.hi[d]);
   }
   if (!__all_sync(0xffffffffu, ok)) {
-    if (lane == 0) lowrank_store(prm, w, prm.oob_value);
+    if (lane == 0) lowrank_store(prm, w, 0.0, true);
     return;
   }
   double* zs = zv[warp];
   double* vs = zs + QP;
   for (int a = lane; a < QP; a += 32) {
-    zs[a] = a < Q ? prm.z_mean[w * Q + a] : 0.0;
-    vs[a] = a < Q ? prm.z_var[w * Q + a] : 0.0;
+    zs[a] = a < Q ? prm.z_mean[w * prm.ldz + prm.z_off + a] : 0.0;
+    vs[a] = a < Q ? prm.z_var[w * prm.ldz + prm.z_off + a] : 0.0;
   }
   __syncwarp();
 
@@ -236,7 +251,7 @@ __global__ void __launch_bounds__(kLrWarps * 32) lowrank_loglike_reg_kernel(cons
   logdet2 = warp_sum(logdet2);
   if (lane == 0) {
     if (!pd) {
-      lowrank_store(prm, w, prm.oob_value);
+      lowrank_store(prm, w, 0.0, true);
       if (prm.n_notpd) atomicAdd(prm.n_notpd, 1);
     } else {
       lowrank_store(prm, w, -0.5 * (prm.s_perp + quad) - 0.5 * logdet2 - prm.logdetF_half + prm.sys_const);

@@ -284,7 +284,35 @@ def lowrank_factors(states, y_exp, cov_exp):
     """Host set-up (once per chain) of the exact low-rank form used by lowrank_loglike.cuh:
         C_w = F + U^T diag(v_w) U,  F = blockdiag(Ctrunc_e) + cov_exp,  U = blockdiag(A_e)
         L_F^-1 U^T = Qb R,  c0 = Qb^T L_F^-1 (mu - y_exp),  s_perp = |(I - Qb Qb^T) L_F^-1 (mu - y_exp)|^2
-    (reference quantities: src/emulator.py:335-363, src/mcmc.py:153-166, 288-290)."""
+    (reference quantities: src/emulator.py:335-363, src/mcmc.py:153-166, 288-290).
+    When cov_exp does not couple the emulators (block diagonal, e.g. the diagonal matrix the reference
+    reads from its pickle) the factorisation is done per emulator: R comes out exactly block diagonal
+    and the device evaluates log L as a sum over emulator blocks."""
+    M = sum(s.m for s in states)
+    Q = sum(s.q for s in states)
+    cov_exp = np.asarray(cov_exp, dtype=np.float64)
+    mask = np.zeros((M, M), dtype=bool)
+    mo = 0
+    for s in states:
+        mask[mo:mo + s.m, mo:mo + s.m] = True
+        mo += s.m
+    if len(states) > 1 and not np.any(cov_exp[~mask]):
+        R, c0, s_perp, ld = np.zeros((Q, Q)), np.empty(Q), 0.0, 0.0
+        qo = mo = 0
+        for s in states:
+            part = _lowrank_factors_joint([s], y_exp[mo:mo + s.m], cov_exp[mo:mo + s.m, mo:mo + s.m])
+            R[qo:qo + s.q, qo:qo + s.q] = part["R"]
+            c0[qo:qo + s.q] = part["c0"]
+            s_perp += part["s_perp"]
+            ld += part["logdetF_half"]
+            qo += s.q
+            mo += s.m
+        return dict(R=np.ascontiguousarray(R), c0=np.ascontiguousarray(c0), s_perp=float(s_perp),
+                    logdetF_half=float(ld))
+    return _lowrank_factors_joint(states, y_exp, cov_exp)
+
+
+def _lowrank_factors_joint(states, y_exp, cov_exp):
     from scipy.linalg import cholesky, qr, solve_triangular
     M = sum(s.m for s in states)
     Q = sum(s.q for s in states)
