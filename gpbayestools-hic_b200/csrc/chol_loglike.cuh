@@ -226,28 +226,37 @@ __global__ void __launch_bounds__(kChThreads, 2) chol_loglike_kernel(const CholP
     }
     __syncthreads();
     if (*s_bad) break;
-    // 4. rows below the diagonal block: P[r, :] <- P[r, :] Dinv^T  (DMMA; blocks 2.. dealt to warps)
-    for (int blk = 2 + warp; blk < nblk; blk += kChWarps) {
-      double a[4], acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-      double* prow = P + (size_t)(8 * blk + g) * kChLd;
-#pragma unroll
-      for (int s = 0; s < 4; s++) a[s] = prow[4 * s + t];
-      __syncwarp();  // every lane has read its row fragment before anyone overwrites the rows
+    // 4. rows below the diagonal block: P[r, :] <- P[r, :] Dinv^T  (DMMA; blocks 2.. dealt to warps
+    //    1..7, the B fragments of Dinv^T held in registers).  Warp 0 meanwhile puts the factor of the
+    //    diagonal block into P's first 16 rows and finishes t[J:J+16] = Dinv * red.
+    if (warp > 0) {
+      double bfr[2][4];
 #pragma unroll
       for (int s = 0; s < 4; s++) {
-        dmma884(acc[0][0], acc[0][1], a[s], Dinv[(size_t)g * kChLd + 4 * s + t]);
-        dmma884(acc[1][0], acc[1][1], a[s], Dinv[(size_t)(8 + g) * kChLd + 4 * s + t]);
+        bfr[0][s] = Dinv[(size_t)g * kChLd + 4 * s + t];
+        bfr[1][s] = Dinv[(size_t)(8 + g) * kChLd + 4 * s + t];
       }
+      for (int blk = 2 + (warp - 1); blk < nblk; blk += kChWarps - 1) {
+        double a[4], acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        double* prow = P + (size_t)(8 * blk + g) * kChLd;
 #pragma unroll
-      for (int h = 0; h < 2; h++) {
-        prow[8 * h + 2 * t] = acc[h][0];
-        prow[8 * h + 2 * t + 1] = acc[h][1];
+        for (int s = 0; s < 4; s++) a[s] = prow[4 * s + t];
+        __syncwarp();  // every lane has read its row fragment before anyone overwrites the rows
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+          dmma884(acc[0][0], acc[0][1], a[s], bfr[0][s]);
+          dmma884(acc[1][0], acc[1][1], a[s], bfr[1][s]);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          prow[8 * h + 2 * t] = acc[h][0];
+          prow[8 * h + 2 * t + 1] = acc[h][1];
+        }
       }
-    }
-    //    the factor of the diagonal block replaces P's first 16 rows; t[J:J+16] = Dinv * red
-    if (warp == kChWarps - 1) {
-      for (int idx = lane; idx < kChNB * kChNB; idx += 32) {
-        const int rr = idx / kChNB, cc = idx - rr * kChNB;
+    } else {
+#pragma unroll
+      for (int i = 0; i < kChNB * kChNB / 32; i++) {
+        const int idx = lane + 32 * i, rr = idx >> 4, cc = idx & 15;
         P[rr * kChLd + cc] = D[rr * kChLd + cc];
       }
       if (lane < nb) {

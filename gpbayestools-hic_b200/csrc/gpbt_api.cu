@@ -12,6 +12,7 @@
 #include "../../include/gpbt.h"
 #include "backtransform.cuh"
 #include "chol_loglike.cuh"
+#include "chol_staged.cuh"
 #include "chol_warp.cuh"
 #include "common.cuh"
 #include "lowrank_loglike.cuh"
@@ -114,6 +115,11 @@ struct gpbt_chain {
   std::vector<int> q_off, m_off;
   int p, Q, M, device;
   bool has_lowrank, has_diag;
+  // cov_exp does not couple the emulators (and every emulator is PCA-mode): the dense path lets
+  // kernel (b) start from base_like[e] = Ctrunc_e + cov_exp[block e], so kernel (c) reads finished
+  // covariances and needs no cov_add pass
+  bool exp_blockdiag = false;
+  std::vector<double*> base_like;
   bool lr_separable = false;          // R is block diagonal over the emulators
   std::vector<double*> R_blocks;      // per-emulator q_e x q_e copies of the diagonal blocks of R
   double s_perp, logdetF_half;
@@ -343,12 +349,12 @@ int run_pc_predict(gpbt_emulator_t e, const double* X, const double* extra, doub
 
 int run_backtransform(gpbt_emulator_t e, const double* zm, const double* zv, int64_t ldz, double* mean,
                       int64_t ld_mean, double* cov, int64_t ld_cov, int64_t col_off, int64_t N,
-                      cudaStream_t st, double* var_diag = nullptr) {
+                      cudaStream_t st, double* var_diag = nullptr, const double* base = nullptr) {
   if (N <= 0) return 0;
   BacktransformParams prm;
   prm.var_diag = var_diag;
   prm.z_mean = zm; prm.z_var = zv; prm.A = e->A; prm.mu = e->mu; prm.scale = e->scale;
-  prm.Ctrunc = e->Ctrunc; prm.mean = mean; prm.cov = cov; prm.ldz = ldz; prm.ld_mean = ld_mean;
+  prm.Ctrunc = base ? base : e->Ctrunc; prm.mean = mean; prm.cov = cov; prm.ldz = ldz; prm.ld_mean = ld_mean;
   prm.ld_cov = ld_cov; prm.col_off = col_off; prm.N = N; prm.q = e->q; prm.m = e->m; prm.m_ld = e->m_ld;
   prm.flags = e->flags;
   backtransform_mean_kernel<<<(unsigned)N, 128, 2 * e->q * sizeof(double), st>>>(prm);
@@ -380,15 +386,26 @@ int run_chol(const double* mean, const double* y_exp, double* cov, const double*
   // Small matrices: warp-per-walker kernel, nine walkers resident per SM (their matrices stay in
   // L2: 1332 x 8m^2 bytes <= ~64 MB).  Larger ones: CTA-per-walker, two per SM -- with more in
   // flight the in-place factors fall out of L2 and every panel update re-reads them from HBM
-  // (measured at m = 300: 3.1 ms vs 1.6 ms per 1024 walkers).  GPBT_CHOL=warp|cta overrides.
+  // (measured at m = 300: 3.1 ms vs 1.6 ms per 1024 walkers).  GPBT_CHOL=warp|staged|cta overrides.
   const char* which = getenv("GPBT_CHOL");
   const size_t wsmem = chol_warp_smem_bytes(m);
   bool use_warp = m <= 80;
   if (which && which[0] == 'w') use_warp = true;
-  if (which && which[0] == 'c') use_warp = false;
+  if (which && (which[0] == 'c' || which[0] == 's')) use_warp = false;
   if (use_warp && wsmem <= (size_t)max_optin_smem()) {
     if (int r = ensure_dynamic_smem<chol_warp_kernel>(wsmem)) return r;
     chol_warp_kernel<<<(unsigned)N, 32, wsmem, st>>>(prm);
+    LAUNCH_CHECK();
+    return 0;
+  }
+  // staged kernel (operand stream through a cp.async ring): needs 16-byte aligned rows and its
+  // fixed block assignment covers m <= 352
+  const size_t ssmem = chol_staged_smem_bytes(m);
+  const bool can_stage = (m % 2 == 0) && m <= kCsMaxM && ((reinterpret_cast<uintptr_t>(cov) & 15) == 0) &&
+                         ssmem <= (size_t)max_optin_smem();
+  if (can_stage && !(which && which[0] == 'c')) {
+    if (int r = ensure_dynamic_smem<chol_staged_kernel>(ssmem)) return r;
+    chol_staged_kernel<<<(unsigned)N, kChThreads, ssmem, st>>>(prm);
     LAUNCH_CHECK();
     return 0;
   }
@@ -579,6 +596,29 @@ extern "C" int gpbt_chain_create(gpbt_chain_t* out, const gpbt_emulator_t* emus,
   h.assign(hi, hi + p); if (int r = upload(&ch->hi, h)) return r;
   h.assign(y_exp, y_exp + ch->M); if (int r = upload(&ch->y_exp, h)) return r;
   h.assign(cov_exp, cov_exp + (size_t)ch->M * ch->M); if (int r = upload(&ch->cov_exp, h)) return r;
+  {
+    bool bd = all_pca;
+    for (int r2 = 0; r2 < ch->M && bd; r2++)
+      for (int c2 = 0; c2 < ch->M; c2++) {
+        int er = 0, ec = 0;
+        while (er + 1 < n_emu && r2 >= ch->m_off[er + 1]) er++;
+        while (ec + 1 < n_emu && c2 >= ch->m_off[ec + 1]) ec++;
+        if (er != ec && cov_exp[(size_t)r2 * ch->M + c2] != 0.0) { bd = false; break; }
+      }
+    ch->exp_blockdiag = bd;
+    if (bd) {
+      for (int e = 0; e < n_emu; e++) {
+        const int m0 = ch->m_off[e], me = emus[e]->m;
+        std::vector<double> ct((size_t)me * me);
+        CU(cudaMemcpy(ct.data(), emus[e]->Ctrunc, ct.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int a = 0; a < me; a++)
+          for (int b2 = 0; b2 < me; b2++) ct[(size_t)a * me + b2] += cov_exp[(size_t)(m0 + a) * ch->M + m0 + b2];
+        double* d = nullptr;
+        if (int r = upload(&d, ct)) return r;
+        ch->base_like.push_back(d);
+      }
+    }
+  }
   ch->R = nullptr; ch->c0 = nullptr;
   if (R) {
     h.assign(R, R + (size_t)ch->Q * ch->Q); if (int r = upload(&ch->R, h)) return r;
@@ -614,6 +654,7 @@ extern "C" int gpbt_chain_create(gpbt_chain_t* out, const gpbt_emulator_t* emus,
 extern "C" int gpbt_chain_destroy(gpbt_chain_t ch) {
   if (!ch) return 0;
   for (double* d : ch->R_blocks) cudaFree(d);
+  for (double* d : ch->base_like) cudaFree(d);
   if (ch->zc_x_host) cudaFreeHost(ch->zc_x_host);
   if (ch->zc_lp_host) cudaFreeHost(ch->zc_lp_host);
   void* ptrs[] = {ch->lo, ch->hi, ch->y_exp, ch->cov_exp, ch->R, ch->c0, ch->z_mean, ch->z_var, ch->extra,
@@ -677,7 +718,7 @@ int ensure_io(gpbt_chain* ch, int64_t N) {
 
 // Chain._predict into (mean, cov) for rows [0, N) of X; cov may be null
 int chain_predict_rows(gpbt_chain* ch, const double* X, double extra_scale, double* mean, double* cov,
-                       int64_t N, cudaStream_t st) {
+                       int64_t N, cudaStream_t st, bool with_exp = false) {
   if (int r = ensure_rows(ch, N)) return r;
   const double* extra = nullptr;
   if (extra_scale != 0.0) {
@@ -690,7 +731,7 @@ int chain_predict_rows(gpbt_chain* ch, const double* X, double extra_scale, doub
     if (int r = run_pc_predict(emu, X, extra, ch->z_mean + ch->q_off[e], ch->z_var + ch->q_off[e], ch->Q, N, st))
       return r;
     if (int r = run_backtransform(emu, ch->z_mean + ch->q_off[e], ch->z_var + ch->q_off[e], ch->Q, mean, ch->M,
-                                  cov, ch->M, ch->m_off[e], N, st))
+                                  cov, ch->M, ch->m_off[e], N, st, nullptr, with_exp ? ch->base_like[e] : nullptr))
       return r;
   }
   return 0;
@@ -839,9 +880,10 @@ int log_posterior_impl(gpbt_chain_t ch, const double* X, double oob_value, doubl
     bounds_mask_kernel<<<(unsigned)((nn + 127) / 128), 128, 0, st>>>(Xs, ch->lo, ch->hi, ch->p, nn, oob_value,
                                                                      ch->skip, lp + s);
     LAUNCH_CHECK();
-    if (int r = chain_predict_rows(ch, Xs, 0.0, ch->mean, ch->cov, nn, st)) return r;
-    if (int r = run_chol(ch->mean, ch->y_exp, ch->cov, ch->cov_exp, lp + s, n_notpd, ch->skip, oob_value,
-                         kSysConst, nn, ch->M, st))
+    const bool pre = ch->exp_blockdiag;   // kernel (b) already adds the experimental covariance
+    if (int r = chain_predict_rows(ch, Xs, 0.0, ch->mean, ch->cov, nn, st, pre)) return r;
+    if (int r = run_chol(ch->mean, ch->y_exp, ch->cov, pre ? nullptr : ch->cov_exp, lp + s, n_notpd, ch->skip,
+                         oob_value, kSysConst, nn, ch->M, st))
       return r;
   }
   return scatter_result(lp, peers, n_peers, peer_off, N, st);

@@ -206,7 +206,7 @@ def test_invariances():
     # both Cholesky kernels (warp-per-walker for small m, CTA-per-walker otherwise) agree
     dense0 = ch.log_target(X[:300], -np.inf, path="dense")
     try:
-        for which in ("warp", "cta"):
+        for which in ("warp", "cta", "staged"):
             os.environ["GPBT_CHOL"] = which
             assert np.max(np.abs(ch.log_target(X[:300], -np.inf, path="dense") - dense0)) <= 1e-9, which
     finally:

@@ -26,7 +26,7 @@ for case in ("odd_shape", "c1_multi", "c1_nopca", "c1_logexp", "p20_trafo", "c1_
             lp = ch.log_target(X, -np.inf, path=path)
             assert np.max(np.abs(lp[fin] - ref[fin])) <= 1e-8, (case, path, tile)
     os.environ.pop("GPBT_PC_TILE")
-    for which in ("warp", "cta"):
+    for which in ("warp", "cta", "staged"):
         os.environ["GPBT_CHOL"] = which
         lp = ch.log_target(X[:9], -np.inf, path="dense")
         mean, cov = ch.predict(X[g["inside"]][:5], 0.05)
