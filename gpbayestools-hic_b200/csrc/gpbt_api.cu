@@ -15,6 +15,7 @@
 #include "chol_staged.cuh"
 #include "chol_warp.cuh"
 #include "common.cuh"
+#include "ensemble.cuh"
 #include "lowrank_loglike.cuh"
 #include "param_trafo.cuh"
 #include "pc_predict.cuh"
@@ -25,6 +26,8 @@ namespace {
 
 thread_local std::string g_err;
 std::atomic<int64_t> g_launches{0};
+// bumped whenever a workspace is reallocated: captured CUDA graphs that hold the old pointers are stale
+std::atomic<int64_t> g_ws_generation{0};
 
 int fail(int code, const char* fmt, ...) {
   char buf[512];
@@ -91,6 +94,11 @@ int ensure_dynamic_smem(size_t bytes) {
   const int dev = current_device();
   if (dev >= 0 && dev < kMaxDevices && bytes <= configured[dev]) return 0;
   CU(cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  // ask for the largest shared-memory carve-out explicitly: kernels launched from a captured graph do
+  // not get the per-launch carve-out heuristic of stream launches, and the kernels that come through
+  // here are sized for a given number of resident CTAs per SM
+  if (bytes > 48 * 1024)
+    CU(cudaFuncSetAttribute(Kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   if (dev >= 0 && dev < kMaxDevices) configured[dev] = bytes;
   return 0;
 }
@@ -333,6 +341,7 @@ int run_pc_predict(gpbt_emulator_t e, const double* X, const double* extra, doub
       if (e->theta) cudaFree(e->theta);
       e->theta_cap = std::max<int64_t>(N, 2 * e->theta_cap);
       CU(cudaMalloc(&e->theta, (size_t)e->theta_cap * e->p * sizeof(double)));
+      g_ws_generation++;
     }
     ParamTrafoParams T = e->trafo;
     T.X = X; T.theta = e->theta; T.N = N;
@@ -681,6 +690,7 @@ int ensure_rows(gpbt_chain* ch, int64_t N) {
   CU(cudaMalloc(&ch->skip, (size_t)cap));
   ch->ws_bytes += (cap - ch->cap_rows) * (2 * ch->Q * 8 + 9);
   ch->cap_rows = cap;
+  g_ws_generation++;
   return 0;
 }
 
@@ -702,6 +712,7 @@ int ensure_dense(gpbt_chain* ch, int64_t rows) {
   CU(cudaMalloc(&ch->cov, (size_t)rows * ch->M * ch->M * sizeof(double)));
   ch->ws_bytes += (rows - ch->cap_dense) * ((int64_t)ch->M * ch->M * 8 + (int64_t)ch->M * 8);
   ch->cap_dense = rows;
+  g_ws_generation++;
   return 0;
 }
 
@@ -754,7 +765,8 @@ extern "C" int gpbt_chain_predict(gpbt_chain_t ch, const double* X, double extra
 
 namespace {
 int log_posterior_impl(gpbt_chain_t ch, const double* X, double oob_value, double* lp, int* n_notpd, int64_t N,
-                       int path, void* stream, double* const* peers, int n_peers, int64_t peer_off);
+                       int path, void* stream, double* const* peers, int n_peers, int64_t peer_off,
+                       bool zero_counter = true);
 
 int scatter_result(const double* lp, double* const* peers, int n_peers, int64_t peer_off, int64_t N, cudaStream_t st) {
   if (n_peers <= 0 || N <= 0) return 0;
@@ -782,7 +794,7 @@ extern "C" int gpbt_log_posterior_scatter(gpbt_chain_t ch, const double* X, doub
 
 namespace {
 int log_posterior_impl(gpbt_chain_t ch, const double* X, double oob_value, double* lp, int* n_notpd, int64_t N,
-                       int path, void* stream, double* const* peers, int n_peers, int64_t peer_off) {
+                       int path, void* stream, double* const* peers, int n_peers, int64_t peer_off, bool zero_counter) {
   if (!ch || !X || !lp || N < 0) return fail(GPBT_EINVAL, "gpbt_log_posterior: bad argument");
   if (ch->device != current_device())
     return fail(GPBT_EINVAL, "chain lives on device %d, current device is %d", ch->device, current_device());
@@ -794,7 +806,7 @@ int log_posterior_impl(gpbt_chain_t ch, const double* X, double oob_value, doubl
     return fail(GPBT_ENOTAPPLICABLE, "diagonal path requested but the covariance of this chain is not diagonal");
   if (path == GPBT_PATH_LOWRANK && !ch->has_lowrank)
     return fail(GPBT_ENOTAPPLICABLE, "low-rank path requested but the chain has no low-rank factors");
-  if (n_notpd) CU(cudaMemsetAsync(n_notpd, 0, sizeof(int), st));
+  if (n_notpd && zero_counter) CU(cudaMemsetAsync(n_notpd, 0, sizeof(int), st));
 
   if (path == GPBT_PATH_LOWRANK) {
     if (int r = ensure_rows(ch, N)) return r;
@@ -850,6 +862,7 @@ int log_posterior_impl(gpbt_chain_t ch, const double* X, double oob_value, doubl
       CU(cudaMalloc(&ch->dvar, (size_t)chunk * ch->M * sizeof(double)));
       ch->ws_bytes += (chunk - ch->cap_diag) * (int64_t)ch->M * 16;
       ch->cap_diag = chunk;
+      g_ws_generation++;
     }
     for (int64_t s = 0; s < N; s += chunk) {
       const int64_t nn = std::min(chunk, N - s);
@@ -918,5 +931,287 @@ extern "C" int gpbt_log_posterior_host(gpbt_chain_t ch, const double* X_host, do
   CU(cudaMemcpyAsync(lp_host, ch->lp_dev, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (n_notpd_host) CU(cudaMemcpyAsync(n_notpd_host, ch->notpd_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ---- device-resident ensemble sampler ------------------------------------------------------------
+struct gpbt_ensemble {
+  gpbt_chain_t ch = nullptr;
+  int nw = 0, p = 0, n_half = 0, randomize = 1;
+  double a = 2.0;
+  uint64_t seed = 0;
+  EnsembleCtl* ctl = nullptr;            // device
+  double *x = nullptr, *lp = nullptr, *q = nullptr, *factor = nullptr, *u_acc = nullptr, *lp_new = nullptr;
+  int *perm = nullptr, *notpd_call = nullptr;
+  unsigned int* rec_done = nullptr;      // CTA arrival counter of ensemble_record_kernel
+  unsigned long long* keys = nullptr;    // [nw] split keys of the current step
+  long long *accepted = nullptr, *notpd_total = nullptr;
+  double *hist_x = nullptr, *hist_lp = nullptr;
+  int64_t hist_cap = 0, steps = 0;
+  double* ru = nullptr;                  // device copies of the host random streams of the current run
+  int *rp = nullptr, *perm_in = nullptr;
+  cudaGraphExec_t graph = nullptr;
+  int64_t graph_gen = -1, graph_launches = 0;   // kernels per replay (for gpbt_launch_count)
+  bool has_state = false;
+};
+
+namespace {
+
+EnsembleBuffers ensemble_buffers(const gpbt_ensemble* en) {
+  EnsembleBuffers b;
+  b.ctl = en->ctl; b.seed = en->seed; b.a = en->a;
+  b.nw = en->nw; b.p = en->p; b.n_half = en->n_half; b.randomize = en->randomize;
+  b.perm = en->perm; b.x = en->x; b.lp = en->lp; b.q = en->q; b.factor = en->factor; b.u_acc = en->u_acc;
+  b.lp_new = en->lp_new; b.notpd_call = en->notpd_call; b.notpd_total = en->notpd_total; b.accepted = en->accepted;
+  return b;
+}
+
+// log-posterior of the proposals of one half step; the counter of non-PD covariances is folded and
+// reset by the accept that follows, not by a memset in front
+int ensemble_log_posterior(gpbt_ensemble* en, int ns, cudaStream_t st) {
+  return log_posterior_impl(en->ch, en->q, -INFINITY, en->lp_new, en->notpd_call, ns, GPBT_PATH_AUTO, st, nullptr, 0, 0,
+                            /*zero_counter=*/false);
+}
+
+int ensemble_enqueue_step(gpbt_ensemble* en, cudaStream_t st) {
+  const int nw = en->nw, p = en->p;
+  const EnsembleBuffers b = ensemble_buffers(en);
+  const size_t key_bytes = (size_t)nw * sizeof(unsigned long long);
+  if (nw <= kEnsembleFusedMaxWalkers && !getenv("GPBT_ENSEMBLE_SPLIT_KERNELS")) {
+    // small ensemble: launch latency is the cost, three single-CTA kernels around the two calls
+    ensemble_begin_kernel<<<1, 1024, key_bytes, st>>>(b);
+    LAUNCH_CHECK();
+    if (int r = ensemble_log_posterior(en, en->n_half, st)) return r;
+    ensemble_mid_kernel<<<1, 1024, 0, st>>>(b);
+    LAUNCH_CHECK();
+    if (nw - en->n_half > 0)
+      if (int r = ensemble_log_posterior(en, nw - en->n_half, st)) return r;
+    ensemble_end_kernel<<<1, 1024, 0, st>>>(b, en->ctl);
+    LAUNCH_CHECK();
+    return 0;
+  }
+  ensemble_keys_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(en->ctl, en->seed, nw, en->randomize, en->keys,
+                                                                    en->perm);
+  LAUNCH_CHECK();
+  ensemble_rank_kernel<<<(unsigned)((nw + kRankThreads - 1) / kRankThreads), kRankThreads, 0, st>>>(
+      en->ctl, nw, en->randomize, en->keys, en->perm);
+  LAUNCH_CHECK();
+  for (int half = 0; half < 2; half++) {
+    const int ns = half == 0 ? en->n_half : nw - en->n_half;
+    if (ns == 0) continue;
+    const unsigned grid = (unsigned)((ns + 127) / 128);
+    ensemble_propose_kernel<<<grid, 128, 0, st>>>(b, half);
+    LAUNCH_CHECK();
+    if (int r = ensemble_log_posterior(en, ns, st)) return r;
+    ensemble_accept_kernel<<<grid, 128, 0, st>>>(b, half);
+    LAUNCH_CHECK();
+  }
+  const unsigned rec_grid = (unsigned)std::min<int64_t>(((int64_t)nw * p + 255) / 256, 148);
+  ensemble_record_kernel<<<rec_grid, 256, 0, st>>>(en->ctl, nw, p, en->x, en->lp, en->rec_done);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// History capacity in steps: grown geometrically (or to an explicit reservation) because device
+// allocation is the one slow call on this path (0.4 - 5 ms observed per cudaMalloc / cudaFree pair).
+int ensemble_grow_history(gpbt_ensemble* en, int64_t need, cudaStream_t st, bool exact = false) {
+  if (need <= en->hist_cap) return 0;
+  const int64_t cap = exact ? need : std::max<int64_t>(need, 2 * en->hist_cap);
+  double *hx = nullptr, *hl = nullptr;
+  CU(cudaMalloc(&hx, (size_t)cap * en->nw * en->p * sizeof(double)));
+  CU(cudaMalloc(&hl, (size_t)cap * en->nw * sizeof(double)));
+  if (en->steps > 0) {
+    CU(cudaMemcpyAsync(hx, en->hist_x, (size_t)en->steps * en->nw * en->p * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(hl, en->hist_lp, (size_t)en->steps * en->nw * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  if (en->hist_x) { cudaFree(en->hist_x); cudaFree(en->hist_lp); }
+  en->hist_x = hx; en->hist_lp = hl; en->hist_cap = cap;
+  return 0;
+}
+
+template <typename T>
+int ensemble_stage(T** dst, const T* src_host, size_t count, cudaStream_t st) {
+  if (*dst) { cudaFree(*dst); *dst = nullptr; }
+  if (!src_host) return 0;
+  CU(cudaMalloc(dst, std::max<size_t>(count, 1) * sizeof(T)));
+  CU(cudaMemcpyAsync(*dst, src_host, count * sizeof(T), cudaMemcpyHostToDevice, st));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int gpbt_ensemble_create(gpbt_ensemble_t* out, gpbt_chain_t chain, int n_walkers, double a,
+                                    int randomize_split, uint64_t seed) {
+  if (!out || !chain) return fail(GPBT_EINVAL, "gpbt_ensemble_create: null argument");
+  if (n_walkers < 2) return fail(GPBT_EINVAL, "gpbt_ensemble_create: need at least 2 walkers, got %d", n_walkers);
+  if (!(a > 1.0)) return fail(GPBT_EINVAL, "gpbt_ensemble_create: stretch scale a must be > 1, got %g", a);
+  CU(cudaSetDevice(chain->device));
+  gpbt_ensemble* en = new gpbt_ensemble();
+  en->ch = chain; en->nw = n_walkers; en->p = chain->p; en->n_half = (n_walkers + 1) / 2;
+  en->a = a; en->randomize = randomize_split ? 1 : 0; en->seed = seed;
+  const size_t nw = n_walkers, p = chain->p, nh = en->n_half;
+  cudaError_t e = cudaSuccess;
+  auto A = [&](void** ptr, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(ptr, bytes); };
+  A((void**)&en->ctl, sizeof(EnsembleCtl));
+  A((void**)&en->x, nw * p * 8); A((void**)&en->lp, nw * 8);
+  A((void**)&en->q, nh * p * 8); A((void**)&en->factor, nh * 8); A((void**)&en->u_acc, nh * 8);
+  A((void**)&en->lp_new, nh * 8); A((void**)&en->perm, nw * 4); A((void**)&en->notpd_call, 4);
+  A((void**)&en->accepted, nw * 8); A((void**)&en->notpd_total, 8); A((void**)&en->rec_done, 4);
+  A((void**)&en->keys, nw * 8);
+  if (e == cudaSuccess) e = cudaMemset(en->accepted, 0, nw * 8);
+  if (e == cudaSuccess) e = cudaMemset(en->notpd_total, 0, 8);
+  if (e == cudaSuccess) e = cudaMemset(en->notpd_call, 0, 4);
+  if (e == cudaSuccess) e = cudaMemset(en->rec_done, 0, 4);
+  if (e != cudaSuccess) {
+    gpbt_ensemble_destroy(en);
+    return fail((int)e, "gpbt_ensemble_create: %s", cudaGetErrorString(e));
+  }
+  *out = en;
+  return 0;
+}
+
+extern "C" int gpbt_ensemble_destroy(gpbt_ensemble_t en) {
+  if (!en) return 0;
+  cudaSetDevice(en->ch->device);
+  cudaStreamSynchronize(en->ch->stream);
+  if (en->graph) cudaGraphExecDestroy(en->graph);
+  void* bufs[] = {en->ctl, en->x, en->lp, en->q, en->factor, en->u_acc, en->lp_new, en->perm, en->notpd_call,
+                  en->accepted, en->notpd_total, en->rec_done, en->keys, en->hist_x, en->hist_lp, en->ru, en->rp, en->perm_in};
+  for (void* b : bufs)
+    if (b) cudaFree(b);
+  delete en;
+  return 0;
+}
+
+extern "C" int gpbt_ensemble_set_state(gpbt_ensemble_t en, const double* X_host, const double* lp_host) {
+  if (!en || !X_host) return fail(GPBT_EINVAL, "gpbt_ensemble_set_state: null argument");
+  CU(cudaSetDevice(en->ch->device));
+  cudaStream_t st = en->ch->stream;
+  CU(cudaMemcpyAsync(en->x, X_host, (size_t)en->nw * en->p * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (lp_host) {
+    CU(cudaMemcpyAsync(en->lp, lp_host, (size_t)en->nw * sizeof(double), cudaMemcpyHostToDevice, st));
+  } else {
+    if (int r = gpbt_log_posterior(en->ch, en->x, -INFINITY, en->lp, en->notpd_call, en->nw, GPBT_PATH_AUTO, st))
+      return r;
+  }
+  CU(cudaStreamSynchronize(st));
+  en->has_state = true;
+  return 0;
+}
+
+extern "C" int gpbt_ensemble_get_state(gpbt_ensemble_t en, double* X_host, double* lp_host) {
+  if (!en) return fail(GPBT_EINVAL, "gpbt_ensemble_get_state: null handle");
+  if (!en->has_state) return fail(GPBT_EINVAL, "gpbt_ensemble_get_state: no state set");
+  CU(cudaSetDevice(en->ch->device));
+  cudaStream_t st = en->ch->stream;
+  if (X_host) CU(cudaMemcpyAsync(X_host, en->x, (size_t)en->nw * en->p * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (lp_host) CU(cudaMemcpyAsync(lp_host, en->lp, (size_t)en->nw * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int gpbt_ensemble_run(gpbt_ensemble_t en, int64_t n_steps, const double* u_host,
+                                 const int32_t* partner_host, const int32_t* perm_host, int use_graph) {
+  if (!en || n_steps < 0) return fail(GPBT_EINVAL, "gpbt_ensemble_run: bad argument");
+  if (!en->has_state) return fail(GPBT_EINVAL, "gpbt_ensemble_run: call gpbt_ensemble_set_state first");
+  if ((u_host == nullptr) != (partner_host == nullptr))
+    return fail(GPBT_EINVAL, "gpbt_ensemble_run: u_host and partner_host come together");
+  if (n_steps == 0) return 0;
+  CU(cudaSetDevice(en->ch->device));
+  cudaStream_t st = en->ch->stream;
+  if (int r = ensemble_grow_history(en, en->steps + n_steps, st)) return r;
+  const size_t rows = (size_t)n_steps * 2 * en->n_half;
+  if (int r = ensemble_stage(&en->ru, u_host, rows * 2, st)) return r;
+  if (int r = ensemble_stage(&en->rp, partner_host, rows, st)) return r;
+  if (int r = ensemble_stage(&en->perm_in, perm_host, (size_t)n_steps * en->nw, st)) return r;
+  EnsembleCtl h;
+  h.step = en->steps; h.run_first = en->steps;
+  h.ru = en->ru; h.rp = en->rp; h.perm_in = en->perm_in;
+  h.hist_x = en->hist_x; h.hist_lp = en->hist_lp;
+  CU(cudaMemcpyAsync(en->ctl, &h, sizeof h, cudaMemcpyHostToDevice, st));
+  CU(cudaStreamSynchronize(st));   // h lives on this stack frame
+
+  int64_t done = 0;
+  // graph replay pays off where a step is launch bound; large ensembles (separate-kernel shape) are
+  // compute bound and measured 2 % faster with plain stream launches
+  if (use_graph && en->nw <= kEnsembleFusedMaxWalkers) {
+    if (en->graph && en->graph_gen != g_ws_generation.load()) {
+      cudaGraphExecDestroy(en->graph);
+      en->graph = nullptr;
+    }
+    if (!en->graph) {
+      // the first step runs eagerly, so that every workspace the path needs exists before the capture
+      if (int r = ensemble_enqueue_step(en, st)) return r;
+      done = 1;
+      if (n_steps > 1) {
+        cudaGraph_t g = nullptr;
+        CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+        const int64_t before = g_launches.load();
+        const int r = ensemble_enqueue_step(en, st);
+        en->graph_launches = g_launches.load() - before;
+        g_launches.store(before);   // captured, not launched
+        const cudaError_t ce = cudaStreamEndCapture(st, &g);
+        if (r || ce != cudaSuccess) {
+          if (g) cudaGraphDestroy(g);
+          return r ? r : fail((int)ce, "gpbt_ensemble_run: graph capture failed: %s", cudaGetErrorString(ce));
+        }
+        const cudaError_t ie = cudaGraphInstantiate(&en->graph, g, 0);
+        cudaGraphDestroy(g);
+        if (ie != cudaSuccess) {
+          en->graph = nullptr;
+          return fail((int)ie, "gpbt_ensemble_run: cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+        }
+        en->graph_gen = g_ws_generation.load();
+      }
+    }
+    for (; done < n_steps; done++) {
+      CU(cudaGraphLaunch(en->graph, st));
+      g_launches.fetch_add(en->graph_launches, std::memory_order_relaxed);
+    }
+  } else {
+    for (; done < n_steps; done++)
+      if (int r = ensemble_enqueue_step(en, st)) return r;
+  }
+  CU(cudaStreamSynchronize(st));
+  en->steps += n_steps;
+  return 0;
+}
+
+extern "C" int64_t gpbt_ensemble_steps(gpbt_ensemble_t en) { return en ? en->steps : 0; }
+
+extern "C" int gpbt_ensemble_reserve(gpbt_ensemble_t en, int64_t n_steps) {
+  if (!en || n_steps < 0) return fail(GPBT_EINVAL, "gpbt_ensemble_reserve: bad argument");
+  CU(cudaSetDevice(en->ch->device));
+  return ensemble_grow_history(en, en->steps + n_steps, en->ch->stream, /*exact=*/true);
+}
+
+extern "C" int gpbt_ensemble_read(gpbt_ensemble_t en, int64_t first, int64_t n, double* chain_host, double* lp_host,
+                                  int64_t* accepted_host, int64_t* n_notpd_host) {
+  if (!en || first < 0 || n < 0 || first + n > en->steps)
+    return fail(GPBT_EINVAL, "gpbt_ensemble_read: rows [%lld, %lld) outside the %lld recorded steps",
+                (long long)first, (long long)(first + n), (long long)(en ? en->steps : 0));
+  CU(cudaSetDevice(en->ch->device));
+  cudaStream_t st = en->ch->stream;
+  const size_t row = (size_t)en->nw * en->p;
+  if (chain_host && n > 0)
+    CU(cudaMemcpyAsync(chain_host, en->hist_x + first * row, n * row * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (lp_host && n > 0)
+    CU(cudaMemcpyAsync(lp_host, en->hist_lp + first * en->nw, (size_t)n * en->nw * sizeof(double),
+                       cudaMemcpyDeviceToHost, st));
+  static_assert(sizeof(long long) == sizeof(int64_t), "accepted counters are copied as int64_t");
+  if (accepted_host)
+    CU(cudaMemcpyAsync(accepted_host, en->accepted, (size_t)en->nw * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  if (n_notpd_host) CU(cudaMemcpyAsync(n_notpd_host, en->notpd_total, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int gpbt_ensemble_reset(gpbt_ensemble_t en) {
+  if (!en) return fail(GPBT_EINVAL, "gpbt_ensemble_reset: null handle");
+  CU(cudaSetDevice(en->ch->device));
+  CU(cudaMemsetAsync(en->accepted, 0, (size_t)en->nw * sizeof(long long), en->ch->stream));
+  CU(cudaStreamSynchronize(en->ch->stream));
+  en->steps = 0;
   return 0;
 }

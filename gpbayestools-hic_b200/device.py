@@ -5,6 +5,7 @@ device-memory allocator / stream provider for calls that hand tensors back to th
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -163,6 +164,7 @@ class DeviceChain:
         self._handle = None
         self._checked = self.lowrank is None
         self.lowrank_check = None
+        self._dependents = weakref.WeakSet()   # device samplers bound to the handle
 
     def handle(self):
         if self._handle is None:
@@ -207,6 +209,8 @@ class DeviceChain:
         return lp
 
     def release(self):
+        for dep in list(getattr(self, "_dependents", ())):
+            dep.close()
         if self._handle is not None:
             _lib.lib.gpbt_chain_destroy(self._handle)
             self._handle = None

@@ -163,11 +163,15 @@ class Chain:
 
     # ---- sampler drivers (callers of the hot path; third-party samplers imported lazily) ----
     def run_mcmc(self, nsteps=500, nburnsteps=None, nwalkers=None, status=None, nthin=10,
-                 skip_initial_state_check=False):
-        """emcee affine-invariant ensemble run with the reference's burn-in recipe: half the
-        burn-in from random positions, restart from the best distinct points, second half, then
-        production; the thinned chain is appended to `mcmc_path` (src/mcmc.py:345-426)."""
-        import emcee
+                 skip_initial_state_check=False, sampler="device", seed=None):
+        """Affine-invariant ensemble run with the reference's burn-in recipe: half the burn-in from
+        random positions, restart from the best distinct points, second half, then production; the
+        thinned chain is appended to `mcmc_path` (src/mcmc.py:345-426).
+
+        sampler="device" (default) keeps the walkers on the GPU for the whole run
+        (gpbt_b200.sampler.DeviceEnsembleSampler: stretch move, one CUDA graph per step);
+        sampler="emcee" drives emcee.EnsembleSampler with pool=self as the reference does, one
+        host call per half-ensemble."""
         if nburnsteps is None or nwalkers is None:
             log.error("must specify nburnsteps and nwalkers to start chain")
             return
@@ -175,35 +179,48 @@ class Chain:
         if self.mcmc_path.exists():
             with open(self.mcmc_path, "rb") as fh:
                 stored = pickle.load(fh)
-        sampler = emcee.EnsembleSampler(nwalkers, self.ndim, self.log_posterior, pool=self)
-        kw = dict(skip_initial_state_check=skip_initial_state_check)
+        if sampler == "device":
+            from .sampler import DeviceEnsembleSampler
+            ens = DeviceEnsembleSampler(nwalkers, self.ndim, self.device(), seed=seed)
 
-        def advance(x0, steps):
-            every = status or max(steps // 10, 1)
-            state = None
-            for i, state in enumerate(sampler.sample(x0, iterations=steps, **kw), start=1):
-                if i % every == 0 or i == steps:
-                    af = sampler.acceptance_fraction
-                    log.info("step %d: acceptance fraction: mean %.4f, std %.4f, min %.4f, max %.4f",
-                             i, af.mean(), af.std(), af.min(), af.max())
-            return state
+            def advance(x0, steps):
+                return ens.run_mcmc(x0, steps, status=status, skip_initial_state_check=skip_initial_state_check)
+        elif sampler == "emcee":
+            import emcee
+            ens = emcee.EnsembleSampler(nwalkers, self.ndim, self.log_posterior, pool=self)
+
+            def advance(x0, steps):
+                every = status or max(steps // 10, 1)
+                state = None
+                for i, state in enumerate(ens.sample(x0, iterations=steps,
+                                                     skip_initial_state_check=skip_initial_state_check), start=1):
+                    if i % every == 0 or i == steps:
+                        af = ens.acceptance_fraction
+                        log.info("step %d: acceptance fraction: mean %.4f, std %.4f, min %.4f, max %.4f",
+                                 i, af.mean(), af.std(), af.min(), af.max())
+                return state
+        else:
+            raise ValueError("sampler must be 'device' or 'emcee', got %r" % (sampler,))
 
         if "chain" in stored:
             x0 = stored["chain"][:, -1, :]
         else:
             first = nburnsteps // 2
             advance(self.random_pos(nwalkers), first)
-            best = np.unique(sampler.get_log_prob(flat=True), return_index=True)[1][-nwalkers:]
-            x0 = sampler.get_chain(flat=True)[best]
-            sampler.reset()
+            best = np.unique(ens.get_log_prob(flat=True), return_index=True)[1][-nwalkers:]
+            x0 = ens.get_chain(flat=True)[best]
+            ens.reset()
             x0 = advance(x0, nburnsteps - first)
-            sampler.reset()
+            ens.reset()
         advance(x0, nsteps)
-        thinned = np.swapaxes(sampler.get_chain(), 0, 1)[:, ::nthin, :]   # [walker, step, dim]
+        thinned = np.swapaxes(ens.get_chain(), 0, 1)[:, ::nthin, :]   # [walker, step, dim]
+        self.acceptance_fraction_ = np.asarray(ens.acceptance_fraction)
         self.chain = np.concatenate((stored["chain"], thinned), axis=1) if "chain" in stored else thinned
         stored["chain"] = self.chain
         with open(self.mcmc_path, "wb") as fh:
             pickle.dump(stored, fh)
+        if sampler == "device":
+            ens.close()
 
     def run_pocoMC(self, n_effective=1000, n_active=250, n_prior=2000, sample="tpcn", n_max_steps=200,
                    random_state=42, n_total=5000, n_evidence=5000, pool=None, prior=None):

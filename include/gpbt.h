@@ -163,6 +163,47 @@ int gpbt_log_posterior_scatter(gpbt_chain_t chain, const double* X_dev, double o
 int gpbt_log_posterior_host(gpbt_chain_t chain, const double* X_host, double oob_value,
                             double* lp_host, int* n_notpd_host, int64_t N, int path);
 
+/* ---- device-resident ensemble sampler --------------------------------------------------- *
+ * Replaces emcee.EnsembleSampler(nwalkers, ndim, chain.log_posterior, pool=chain) with its
+ * default stretch move, as driven by LoggingEnsembleSampler.run_mcmc / Chain.run_mcmc
+ * (src/mcmc.py:68-92, 372-412).  Walkers, log-posteriors and the history of every step stay on
+ * the device; a step is a CUDA graph around the log-posterior path, so nothing crosses PCIe
+ * until the chain is read back.  emcee (>= 3.1.4, requirements.txt) is not part of the reference
+ * tree; the move follows the published algorithm (Goodman & Weare 2010; red/blue split).
+ * All calls are synchronous and run on the chain's own stream.                               */
+typedef struct gpbt_ensemble* gpbt_ensemble_t;
+
+/* a: stretch scale (emcee default 2.0); randomize_split: shuffle the two walker sets every
+ * step (emcee default) or keep even / odd walkers apart; seed: Philox key                    */
+int gpbt_ensemble_create(gpbt_ensemble_t* out, gpbt_chain_t chain, int n_walkers, double a,
+                         int randomize_split, uint64_t seed);
+int gpbt_ensemble_destroy(gpbt_ensemble_t ens);
+
+/* walker positions X_host [n_walkers, p]; lp_host [n_walkers] or NULL (= evaluate them)      */
+int gpbt_ensemble_set_state(gpbt_ensemble_t ens, const double* X_host, const double* lp_host);
+int gpbt_ensemble_get_state(gpbt_ensemble_t ens, double* X_host, double* lp_host);
+
+/* Advance n_steps steps, appending every step to the device history.
+ * Test hooks (all NULL in production = device Philox streams): u_host [n_steps, 2, n_half, 2]
+ * uniforms (stretch draw, accept draw) and partner_host [n_steps, 2, n_half] indices into the
+ * complementary set, with n_half = ceil(n_walkers / 2); perm_host [n_steps, n_walkers] the split
+ * permutation of each step (first n_half entries = first set).
+ * use_graph: 0 = enqueue kernel by kernel, 1 = replay a captured CUDA graph.                 */
+int gpbt_ensemble_run(gpbt_ensemble_t ens, int64_t n_steps, const double* u_host,
+                      const int32_t* partner_host, const int32_t* perm_host, int use_graph);
+
+/* steps in the history since the last reset                                                  */
+int64_t gpbt_ensemble_steps(gpbt_ensemble_t ens);
+/* make room for n_steps more steps of history in one allocation (optional; run grows it)     */
+int gpbt_ensemble_reserve(gpbt_ensemble_t ens, int64_t n_steps);
+/* history rows [first, first + n): chain_host [n, n_walkers, p], lp_host [n, n_walkers]
+ * (either may be NULL); accepted_host [n_walkers] accepted proposals per walker since the
+ * last reset; n_notpd_host: non-positive-definite covariances met since creation            */
+int gpbt_ensemble_read(gpbt_ensemble_t ens, int64_t first, int64_t n, double* chain_host,
+                       double* lp_host, int64_t* accepted_host, int64_t* n_notpd_host);
+/* forget the history and the acceptance counts; the walkers stay where they are              */
+int gpbt_ensemble_reset(gpbt_ensemble_t ens);
+
 /* bytes of device workspace the chain currently holds (grows with the largest N seen)        */
 int64_t gpbt_chain_workspace_bytes(gpbt_chain_t chain);
 

@@ -322,7 +322,7 @@ def test_sampler_drives_gpu_posterior(tmp_path, monkeypatch):
     ch = Chain(mcmc_path=str(tmp_path / "mcmc" / "chain.pkl"), expdata_path=paths["exp"], model_parafile=paths["par"])
     ch.emuList = states                       # EmulatorState objects are accepted directly
     np.random.seed(0)
-    ch.run_mcmc(nsteps=12, nburnsteps=8, nwalkers=16, nthin=3)
+    ch.run_mcmc(nsteps=12, nburnsteps=8, nwalkers=16, nthin=3, sampler="emcee")
     with open(ch.mcmc_path, "rb") as fh:
         stored = pickle.load(fh)
     chain = stored["chain"]
@@ -333,7 +333,7 @@ def test_sampler_drives_gpu_posterior(tmp_path, monkeypatch):
     assert np.all(np.isfinite(lp))
     want = orc.log_posterior(sts, flat[:12], ch.min, ch.max, ch.expdata, ch.expdata_cov)
     assert np.max(np.abs(lp[:12] - want)) <= ABS_LP
-    ch.run_mcmc(nsteps=6, nburnsteps=8, nwalkers=16, nthin=3)          # restart from the stored chain
+    ch.run_mcmc(nsteps=6, nburnsteps=8, nwalkers=16, nthin=3, sampler="emcee")          # restart from the stored chain
     with open(ch.mcmc_path, "rb") as fh:
         assert pickle.load(fh)["chain"].shape == (16, 6, 5)
 

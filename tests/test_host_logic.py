@@ -193,3 +193,39 @@ def test_state_extraction_from_a_reference_pickle(tmp_path):
     lp = orc.log_posterior([od], X, ref["lo"], ref["hi"], ref["y"], ref["c"])
     fin = np.isfinite(ref["lp"])
     assert np.array_equal(np.isfinite(lp), fin) and np.max(np.abs(lp[fin] - ref["lp"][fin])) <= 1e-8
+
+
+def test_philox_known_answers():
+    """Philox4x32-10 restatement (oracle/ensemble_oracle.py, mirrored by csrc/ensemble.cuh) against the
+    known-answer vectors published with the generator (Random123 kat_vectors: counter, key -> output)."""
+    from oracle.ensemble_oracle import philox4x32
+
+    def run(ctr, key):
+        return philox4x32(key[0] | (key[1] << 32), ctr[0] | (ctr[1] << 32), ctr[2], ctr[3])
+
+    assert run([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert run([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert run([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_stretch_oracle_samples_a_known_gaussian():
+    """The stretch-move restatement driven by the Philox streams samples a correlated 3-d Gaussian with
+    the right mean and covariance (the published algorithm's invariant distribution)."""
+    from oracle import ensemble_oracle as eo
+    cov = np.array([[1.0, 0.6, 0.0], [0.6, 2.0, -0.5], [0.0, -0.5, 0.5]])
+    mean = np.array([1.0, -2.0, 0.5])
+    P = np.linalg.inv(cov)
+    logp = lambda X: -0.5 * np.einsum("ni,ij,nj->n", X - mean, P, X - mean)
+    nw, steps = 24, 1500
+    u, partner, perm = eo.philox_streams(11, 0, steps, nw)
+    assert u.min() >= 0.0 and u.max() < 1.0 and abs(u.mean() - 0.5) < 0.01
+    assert partner.min() == 0 and partner.max() == nw // 2 - 1
+    x0 = mean + np.random.default_rng(0).normal(size=(nw, 3))
+    chain, lps, acc = eo.stretch_run(logp, x0, logp(x0), u, partner, perm)
+    flat = chain[300:].reshape(-1, 3)
+    assert np.all(np.abs(flat.mean(axis=0) - mean) < 0.1)
+    assert np.max(np.abs(np.cov(flat, rowvar=False) - cov)) < 0.15
+    assert 0.3 < acc.mean() / steps < 0.8
+    np.testing.assert_array_equal(lps[-1], logp(chain[-1]))
+    assert sorted(eo.fixed_split(7)) == list(range(7)) and list(eo.fixed_split(5)) == [0, 2, 4, 1, 3]

@@ -1,0 +1,103 @@
+"""Sampler steps per second: the device-resident ensemble sampler (one CUDA graph per step) against a
+host-side stretch-move loop that calls the GPU log-posterior once per half-ensemble, which is how
+emcee drives the reference (pool=self).  Config 1 (128 walkers on the p5/n100/m50/q10 emulator) is
+latency bound; config 2 (8192 walkers on p17/n500/m300/q20) is throughput bound.
+
+    python tools/bench_sampler.py [out.jsonl]
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import gpbt_b200  # noqa: E402,F401
+from gpbt_b200 import _lib  # noqa: E402
+from gpbt_b200.device import DeviceChain  # noqa: E402
+from gpbt_b200.sampler import DeviceEnsembleSampler  # noqa: E402
+from gpbt_b200.state import EmulatorState  # noqa: E402
+from tests import goldens  # noqa: E402
+
+out = open(sys.argv[1], "w") if len(sys.argv) > 1 else None
+
+
+def emit(d):
+    line = json.dumps(d)
+    print(line)
+    if out:
+        out.write(line + "\n")
+        out.flush()
+
+
+def host_loop(dc, x0, steps, a=2.0, seed=0):
+    """stretch move on the host, two GPU calls per step (the emcee pattern)"""
+    rng = np.random.default_rng(seed)
+    x = x0.copy()
+    nw, p = x.shape
+    half = nw // 2
+    lp = dc.log_target(x, -np.inf)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        for s, c in ((slice(0, half), slice(half, nw)), (slice(half, nw), slice(0, half))):
+            ns = x[s].shape[0]
+            z = ((a - 1.0) * rng.random(ns) + 1.0) ** 2 / a
+            partner = x[c][rng.integers(0, x[c].shape[0], ns)]
+            prop = partner + z[:, None] * (x[s] - partner)
+            lp_new = dc.log_target(prop, -np.inf)
+            acc = np.log(rng.random(ns)) < (p - 1) * np.log(z) + lp_new - lp[s]
+            xs, ls = x[s].copy(), lp[s].copy()
+            xs[acc], ls[acc] = prop[acc], lp_new[acc]
+            x[s], lp[s] = xs, ls
+    return steps / (time.perf_counter() - t0)
+
+
+def device_rate(dc, x0, steps, use_graph):
+    s = DeviceEnsembleSampler(x0.shape[0], x0.shape[1], dc, seed=1, use_graph=use_graph)
+    s.set_state(x0)
+    s.advance(min(steps, 50))                      # warm-up (workspaces, graph capture)
+    l0 = _lib.lib.gpbt_launch_count()
+    t0 = time.perf_counter()
+    s.advance(steps)
+    dt = time.perf_counter() - t0
+    launches = (_lib.lib.gpbt_launch_count() - l0)
+    af = float(s.acceptance_fraction.mean())
+    s.close()
+    return steps / dt, af, launches
+
+
+def start(lo, hi, nw, seed=5):
+    rng = np.random.default_rng(seed)
+    mid, half = 0.5 * (lo + hi), 0.5 * (hi - lo)
+    return mid + 0.5 * half * rng.uniform(-1, 1, (nw, len(mid)))
+
+
+def run(name, dc, lo, hi, nw, steps, host_steps):
+    x0 = start(lo, hi, nw)
+    for use_graph in (True, False):
+        rate, af, launches = device_rate(dc, x0, steps, use_graph)
+        emit({"config": name, "walkers": nw, "sampler": "device, " + ("CUDA graph per step" if use_graph else "eager launches"),
+              "steps_per_s": rate, "evals_per_s": rate * nw, "us_per_step": 1e6 / rate, "acceptance": af,
+              "kernel_launches_enqueued": int(launches), "steps": steps})
+    rate = host_loop(dc, x0, host_steps)
+    emit({"config": name, "walkers": nw, "sampler": "host stretch-move loop, 2 GPU calls per step (emcee pattern)",
+          "steps_per_s": rate, "evals_per_s": rate * nw, "us_per_step": 1e6 / rate, "steps": host_steps})
+
+
+g = goldens.load("c1_rbf")
+sts = goldens.oracle_states(g)
+states = [EmulatorState.from_arrays(s["kind"], s["Xtr"], s["ell"], s["c"], s["sn"], s["alpha"], s["mu"], s["scale"],
+                                    s.get("A"), s.get("Ctrunc"), L=s["L"], keep_L=False) for s in sts]
+dc = DeviceChain(states, g["lo"], g["hi"], g["y_exp"].reshape(-1), g["cov_exp"])
+run("C1 (p5,n100,m50,q10)", dc, g["lo"], g["hi"], 128, 5000, 2000)
+dc.release()
+
+g2 = goldens.load("c2_rbf")
+sts2 = goldens.oracle_states(g2)
+states2 = [EmulatorState.from_arrays(s["kind"], s["Xtr"], s["ell"], s["c"], s["sn"], s["alpha"], s["mu"], s["scale"],
+                                     s.get("A"), s.get("Ctrunc"), L=s["L"], keep_L=False) for s in sts2]
+dc = DeviceChain(states2, g2["lo"], g2["hi"], g2["y_exp"].reshape(-1), g2["cov_exp"])
+run("C2 (p17,n500,m300,q20)", dc, g2["lo"], g2["hi"], 8192, 300, 100)
+dc.release()
