@@ -222,6 +222,31 @@ class Chain:
         if sampler == "device":
             ens.close()
 
+    # ---- parallel tempering (src/mcmc.py:431-727) -----------------------------------------
+    def samplerPTLMC(self, logpostfunc, draw_func, theta0=None, numtemps=32, numchain=16, sampperchain=400,
+                     maxtemp=30, nstartparameters=1000):
+        """Parallel-tempering (Langevin) MCMC; returns {'theta': [numchain, sampperchain, p]}.
+        See gpbt_b200.ptlmc for the algorithm."""
+        from .ptlmc import sampler_ptlmc
+        return sampler_ptlmc(logpostfunc, draw_func, theta0=theta0, numtemps=numtemps, numchain=numchain,
+                             sampperchain=sampperchain, maxtemp=maxtemp, nstartparameters=nstartparameters,
+                             exchange=self.tempexchange)
+
+    def tempexchange(self, lpostf, temps, iters=1):
+        from .ptlmc import temp_exchange
+        return temp_exchange(lpostf, temps, iters=iters)
+
+    def run_MCMC_PTLMC(self, nsteps=500, nwalkers=16, ntemps=50, maxtemp=100, nstartparameters=1000):
+        """PTLMC run on the GPU log-posterior (all ntemps + nwalkers chains in one call per iteration);
+        the T = 1 chains are stored as chain[nwalkers, nsteps, ndim] in `mcmc_path`
+        (src/mcmc.py:696-727)."""
+        out = self.samplerPTLMC(logpostfunc=self.log_posterior, draw_func=self.random_pos, theta0=None,
+                                numtemps=ntemps, numchain=nwalkers, sampperchain=nsteps, maxtemp=maxtemp,
+                                nstartparameters=nstartparameters)
+        self.chain = out["theta"].reshape((nwalkers, nsteps, self.ndim))
+        with open(self.mcmc_path, "wb") as fh:
+            pickle.dump({"chain": self.chain}, fh)
+
     def run_pocoMC(self, n_effective=1000, n_active=250, n_prior=2000, sample="tpcn", n_max_steps=200,
                    random_state=42, n_total=5000, n_evidence=5000, pool=None, prior=None):
         """pocoMC preconditioned Monte Carlo with a uniform prior on the box (src/mcmc.py:752-819).

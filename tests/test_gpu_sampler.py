@@ -200,3 +200,29 @@ def test_argument_errors(c1):
     dc.release()                                            # releasing the chain closes its samplers
     with pytest.raises(RuntimeError):
         s.advance(1)
+
+
+def test_run_mcmc_ptlmc_on_gpu_posterior(tmp_path):
+    """Chain.run_MCMC_PTLMC (src/mcmc.py:696-727): the parallel-tempering driver on the GPU
+    log-posterior -- N = 1 and N = 2 probe calls, N = 1 calls from L-BFGS-B, one call of all chains
+    per iteration; chain file layout [nwalkers, nsteps, ndim], T = 1 chains inside the box."""
+    from gpbt_b200 import synthetic
+    from gpbt_b200.mcmc import Chain
+    g = goldens.load("c1_rbf")
+    states, sts = product_states(g)
+    (tmp_path / "mcmc").mkdir()
+    paths = synthetic.write_fixture(str(tmp_path), p=5, n=8, m=50)
+    ch = Chain(mcmc_path=str(tmp_path / "mcmc" / "pt.pkl"), expdata_path=paths["exp"], model_parafile=paths["par"])
+    ch.emuList = states
+    np.random.seed(1)
+    ch.run_MCMC_PTLMC(nsteps=20, nwalkers=4, ntemps=6, maxtemp=20, nstartparameters=80)
+    with open(ch.mcmc_path, "rb") as fh:
+        chain = pickle.load(fh)["chain"]
+    assert chain.shape == (4, 20, 5)
+    flat = chain.reshape(-1, 5)
+    assert np.all((flat > ch.min) & (flat < ch.max))
+    lp = ch.log_posterior(flat)
+    want = orc.log_posterior(sts, flat[:10], ch.min, ch.max, ch.expdata, ch.expdata_cov)
+    assert np.all(np.isfinite(lp)) and np.max(np.abs(lp[:10] - want)) <= ABS_LP
+    # the optimiser and the tempered chains have moved to high-posterior territory
+    assert np.median(lp) > np.median(ch.log_posterior(ch.random_pos(200)))
