@@ -8,14 +8,14 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgpbt_b200.so")
 
-KERNEL_RBF, KERNEL_MATERN32 = 0, 1
+KERNEL_RBF, KERNEL_MATERN32, KERNEL_PCGP = 0, 1, 2
 FLAG_NO_PCA, FLAG_EXP_DIAG = 1, 2
 PATH_AUTO, PATH_DENSE, PATH_LOWRANK, PATH_DIAG = 0, 1, 2, 3
 
 # every symbol include/gpbt.h declares (tests/test_cabi.py checks the library exports them all)
 SYMBOLS = [
     "gpbt_last_error", "gpbt_version", "gpbt_emulator_create", "gpbt_emulator_destroy",
-    "gpbt_emulator_set_param_trafo", "gpbt_emulator_input_dim",
+    "gpbt_emulator_create_pcgp", "gpbt_emulator_set_param_trafo", "gpbt_emulator_input_dim",
     "gpbt_pc_predict", "gpbt_backtransform", "gpbt_backtransform_diag", "gpbt_mvn_loglike", "gpbt_chain_create",
     "gpbt_chain_destroy", "gpbt_chain_predict", "gpbt_log_posterior", "gpbt_log_posterior_scatter",
     "gpbt_log_posterior_host",
@@ -41,6 +41,7 @@ def _load():
     lib.gpbt_launch_count.restype = i64
     lib.gpbt_emulator_create.argtypes = [C.POINTER(vp), i32, i32, i32, i32, i32, i32] + [dp] * 10
     lib.gpbt_emulator_destroy.argtypes = [vp]
+    lib.gpbt_emulator_create_pcgp.argtypes = [C.POINTER(vp), i32, i32, i32, i32, i32] + [dp] * 10
     lib.gpbt_emulator_set_param_trafo.argtypes = [vp, i32, dp, i32, i32, dp, dp, dp, dp, dp, dp, dp, dp]
     lib.gpbt_emulator_input_dim.argtypes = [vp]
     lib.gpbt_pc_predict.argtypes = [vp, dp, dp, dp, dp, i64, i64, vp]

@@ -108,6 +108,7 @@ int ensure_dynamic_smem(size_t bytes) {
 struct gpbt_emulator {
   int p, p_pad, n, n_pad, q, q_pad, m, m_ld, kind, flags, device;
   double *Xs, *ell, *c, *sn, *W, *A, *mu, *scale, *Ctrunc;
+  double* sig2;           // PCGP kind only
   // optional parameter-function PCA pre-transform: X [N, p_in] -> theta [N, p]
   bool has_trafo;
   int p_in;
@@ -158,6 +159,12 @@ extern "C" int64_t gpbt_launch_count(void) { return g_launches.load(); }
 // ------------------------------------------------------------------------------------------------
 // emulator state
 // ------------------------------------------------------------------------------------------------
+namespace {
+int emulator_upload(gpbt_emulator* e, int p, int n, int q, int m, int kernel_kind, int flags, const double* Xtr,
+                    const double* ell, const double* c, const double* sn, const double* alpha, const double* Linv,
+                    const double* A, const double* mu, const double* scale, const double* Ctrunc);
+}
+
 extern "C" int gpbt_emulator_create(gpbt_emulator_t* out, int p, int n, int q, int m, int kernel_kind,
                                     int flags, const double* Xtr, const double* ell, const double* c,
                                     const double* sn, const double* alpha, const double* Linv,
@@ -166,13 +173,28 @@ extern "C" int gpbt_emulator_create(gpbt_emulator_t* out, int p, int n, int q, i
   if (!out || p <= 0 || n <= 0 || q <= 0 || m <= 0 || !Xtr || !ell || !c || !sn || !alpha || !Linv || !mu)
     return fail(GPBT_EINVAL, "gpbt_emulator_create: null or non-positive argument");
   if (kernel_kind != GPBT_KERNEL_RBF && kernel_kind != GPBT_KERNEL_MATERN32)
-    return fail(GPBT_EINVAL, "gpbt_emulator_create: unknown kernel kind %d", kernel_kind);
+    return fail(GPBT_EINVAL, "gpbt_emulator_create: unknown kernel kind %d (PCGP emulators: gpbt_emulator_create_pcgp)",
+                kernel_kind);
   const bool no_pca = flags & GPBT_FLAG_NO_PCA;
   if (no_pca && (q != m || !scale)) return fail(GPBT_EINVAL, "no-PCA mode needs q == m and scale");
   if (!no_pca && (!A || !Ctrunc)) return fail(GPBT_EINVAL, "PCA mode needs A and Ctrunc");
 
   gpbt_emulator* e = new gpbt_emulator();
   memset(e, 0, sizeof *e);
+  const int rc = emulator_upload(e, p, n, q, m, kernel_kind, flags, Xtr, ell, c, sn, alpha, Linv, A, mu, scale, Ctrunc);
+  if (rc) {   // nothing half-built escapes: the error message set by the failing call survives
+    gpbt_emulator_destroy(e);
+    return rc;
+  }
+  *out = e;
+  return 0;
+}
+
+namespace {
+int emulator_upload(gpbt_emulator* e, int p, int n, int q, int m, int kernel_kind, int flags, const double* Xtr,
+                    const double* ell, const double* c, const double* sn, const double* alpha, const double* Linv,
+                    const double* A, const double* mu, const double* scale, const double* Ctrunc) {
+  const bool no_pca = flags & GPBT_FLAG_NO_PCA;
   e->p = p; e->n = n; e->q = q; e->m = m; e->kind = kernel_kind; e->flags = flags;
   e->p_pad = (int)round_up(p, 2);
   e->n_pad = (int)round_up(n, 32);
@@ -203,9 +225,11 @@ extern "C" int gpbt_emulator_create(gpbt_emulator_t* out, int p, int n, int q, i
   h.assign(sn, sn + q);
   if (int r = upload(&e->sn, h)) return r;
   h.assign((size_t)q * NP * NP, 0.0);
+  const bool dense_w = kernel_kind == GPBT_KERNEL_PCGP;   // full rows, not just the lower triangle
   for (int j = 0; j < q; j++)
     for (int i = 0; i < n; i++)
-      memcpy(&h[((size_t)j * NP + i) * NP], Linv + ((size_t)j * n + i) * n, (size_t)(i + 1) * sizeof(double));
+      memcpy(&h[((size_t)j * NP + i) * NP], Linv + ((size_t)j * n + i) * n,
+             (size_t)(dense_w ? n : i + 1) * sizeof(double));
   if (int r = upload(&e->W, h)) return r;
   h.assign(mu, mu + m);
   if (int r = upload(&e->mu, h)) return r;
@@ -220,6 +244,31 @@ extern "C" int gpbt_emulator_create(gpbt_emulator_t* out, int p, int n, int q, i
     h.assign(Ctrunc, Ctrunc + (size_t)m * m);
     if (int r = upload(&e->Ctrunc, h)) return r;
   }
+  return 0;
+}
+}  // namespace
+
+extern "C" int gpbt_emulator_create_pcgp(gpbt_emulator_t* out, int p, int n, int q, int m, int flags,
+                                         const double* theta, const double* ell, const double* amp,
+                                         const double* off, const double* sig2, const double* pw,
+                                         const double* VhT, const double* A, const double* offset,
+                                         const double* extra_cov) {
+  if (!out || p <= 0 || n <= 0 || q <= 0 || m <= 0 || !theta || !ell || !amp || !off || !sig2 || !pw || !VhT || !A ||
+      !offset || !extra_cov)
+    return fail(GPBT_EINVAL, "gpbt_emulator_create_pcgp: null or non-positive argument");
+  if (flags & GPBT_FLAG_NO_PCA) return fail(GPBT_EINVAL, "gpbt_emulator_create_pcgp: there is no no-PCA mode");
+  gpbt_emulator* e = new gpbt_emulator();
+  memset(e, 0, sizeof *e);
+  int rc = emulator_upload(e, p, n, q, m, GPBT_KERNEL_PCGP, flags, theta, ell, amp, off, pw, VhT, A, offset, nullptr,
+                           extra_cov);
+  if (!rc) {
+    std::vector<double> h(sig2, sig2 + q);
+    rc = upload(&e->sig2, h);
+  }
+  if (rc) {
+    gpbt_emulator_destroy(e);
+    return rc;
+  }
   *out = e;
   return 0;
 }
@@ -233,6 +282,10 @@ extern "C" int gpbt_emulator_set_param_trafo(gpbt_emulator_t e, int p_in, const 
   int p_out = n_keep;
   for (int g = 0; g < n_groups; g++) p_out += ncomp[g];
   if (p_out != e->p) return fail(GPBT_EINVAL, "param trafo produces %d columns, emulator was trained on %d", p_out, e->p);
+  e->has_trafo = false;   // a second call replaces the first transform
+  if (e->keep_dev) { cudaFree(e->keep_dev); e->keep_dev = nullptr; }
+  for (double*& buf : e->trafo_buf)
+    if (buf) { cudaFree(buf); buf = nullptr; }
   ParamTrafoParams& T = e->trafo;
   memset(&T, 0, sizeof T);
   T.p_in = p_in; T.p_out = p_out; T.n_keep = n_keep; T.n_groups = n_groups;
@@ -270,7 +323,7 @@ extern "C" int gpbt_emulator_destroy(gpbt_emulator_t e) {
   if (e->theta) cudaFree(e->theta);
   for (double* p : e->trafo_buf)
     if (p) cudaFree(p);
-  double* ptrs[] = {e->Xs, e->ell, e->c, e->sn, e->W, e->A, e->mu, e->scale, e->Ctrunc};
+  double* ptrs[] = {e->Xs, e->ell, e->c, e->sn, e->W, e->A, e->mu, e->scale, e->Ctrunc, e->sig2};
   for (double* p : ptrs)
     if (p) cudaFree(p);
   delete e;
@@ -339,8 +392,11 @@ int run_pc_predict(gpbt_emulator_t e, const double* X, const double* extra, doub
       // (stream-ordered work that still reads the old buffer has been enqueued before this free;
       // cudaFree synchronises the device)
       if (e->theta) cudaFree(e->theta);
-      e->theta_cap = std::max<int64_t>(N, 2 * e->theta_cap);
-      CU(cudaMalloc(&e->theta, (size_t)e->theta_cap * e->p * sizeof(double)));
+      e->theta = nullptr;
+      const int64_t cap = std::max<int64_t>(N, 2 * e->theta_cap);
+      e->theta_cap = 0;
+      CU(cudaMalloc(&e->theta, (size_t)cap * e->p * sizeof(double)));
+      e->theta_cap = cap;
       g_ws_generation++;
     }
     ParamTrafoParams T = e->trafo;
@@ -351,9 +407,13 @@ int run_pc_predict(gpbt_emulator_t e, const double* X, const double* extra, doub
   }
   PcPredictParams prm;
   prm.X = X; prm.extra = extra; prm.Xs = e->Xs; prm.ell = e->ell; prm.c = e->c; prm.sn = e->sn;
-  prm.W = e->W; prm.z_mean = zm; prm.z_var = zv; prm.ldz = ldz; prm.N = N;
+  prm.W = e->W; prm.sig2 = e->sig2; prm.z_mean = zm; prm.z_var = zv; prm.ldz = ldz; prm.N = N;
   prm.p = e->p; prm.p_pad = e->p_pad; prm.n = e->n; prm.n_pad = e->n_pad; prm.q = e->q;
-  return e->kind == GPBT_KERNEL_RBF ? dispatch_pc_predict<0>(prm, st) : dispatch_pc_predict<1>(prm, st);
+  switch (e->kind) {
+    case GPBT_KERNEL_RBF: return dispatch_pc_predict<0>(prm, st);
+    case GPBT_KERNEL_MATERN32: return dispatch_pc_predict<1>(prm, st);
+    default: return dispatch_pc_predict<2>(prm, st);
+  }
 }
 
 int run_backtransform(gpbt_emulator_t e, const double* zm, const double* zv, int64_t ldz, double* mean,
@@ -566,6 +626,12 @@ extern "C" int gpbt_mvn_loglike(const double* mean, const double* y_exp, double*
 // ------------------------------------------------------------------------------------------------
 // chain
 // ------------------------------------------------------------------------------------------------
+namespace {
+int chain_build(gpbt_chain* ch, const gpbt_emulator_t* emus, int n_emu, int p, const double* lo, const double* hi,
+                const double* y_exp, const double* cov_exp, const double* R, const double* c0, double s_perp,
+                double logdetF_half);
+}
+
 extern "C" int gpbt_chain_create(gpbt_chain_t* out, const gpbt_emulator_t* emus, int n_emu, int p,
                                  const double* lo, const double* hi, const double* y_exp,
                                  const double* cov_exp, const double* R, const double* c0, double s_perp,
@@ -573,14 +639,25 @@ extern "C" int gpbt_chain_create(gpbt_chain_t* out, const gpbt_emulator_t* emus,
   if (!out || !emus || n_emu <= 0 || !lo || !hi || !y_exp || !cov_exp)
     return fail(GPBT_EINVAL, "gpbt_chain_create: null argument");
   gpbt_chain* ch = new gpbt_chain();
+  const int rc = chain_build(ch, emus, n_emu, p, lo, hi, y_exp, cov_exp, R, c0, s_perp, logdetF_half);
+  if (rc) {
+    gpbt_chain_destroy(ch);
+    return rc;
+  }
+  *out = ch;
+  return 0;
+}
+
+namespace {
+int chain_build(gpbt_chain* ch, const gpbt_emulator_t* emus, int n_emu, int p, const double* lo, const double* hi,
+                const double* y_exp, const double* cov_exp, const double* R, const double* c0, double s_perp,
+                double logdetF_half) {
   ch->p = p; ch->Q = 0; ch->M = 0;
   cudaGetDevice(&ch->device);
   bool all_pca = true;
   for (int i = 0; i < n_emu; i++) {
-    if (!emus[i] || gpbt_emulator_input_dim(emus[i]) != p) {
-      delete ch;
+    if (!emus[i] || gpbt_emulator_input_dim(emus[i]) != p)
       return fail(GPBT_EINVAL, "emulator %d: parameter count mismatch", i);
-    }
     ch->emus.push_back(emus[i]);
     ch->q_off.push_back(ch->Q);
     ch->m_off.push_back(ch->M);
@@ -588,8 +665,9 @@ extern "C" int gpbt_chain_create(gpbt_chain_t* out, const gpbt_emulator_t* emus,
     ch->M += emus[i]->m;
     if (emus[i]->flags & (GPBT_FLAG_NO_PCA | GPBT_FLAG_EXP_DIAG)) all_pca = false;
   }
-  if (R && !all_pca) { delete ch; return fail(GPBT_ENOTAPPLICABLE, "low-rank factors given for a chain with a no-PCA / exp-diag emulator"); }
-  if (R && !c0) { delete ch; return fail(GPBT_EINVAL, "R given without c0"); }
+  if (R && !all_pca)
+    return fail(GPBT_ENOTAPPLICABLE, "low-rank factors given for a chain with a no-PCA / exp-diag emulator");
+  if (R && !c0) return fail(GPBT_EINVAL, "R given without c0");
   ch->has_lowrank = R != nullptr;
   bool all_diag = true;
   for (int i = 0; i < n_emu; i++)
@@ -656,9 +734,9 @@ extern "C" int gpbt_chain_create(gpbt_chain_t* out, const gpbt_emulator_t* emus,
   }
   CU(cudaMalloc(&ch->notpd_dev, sizeof(int)));
   CU(cudaStreamCreateWithFlags(&ch->stream, cudaStreamNonBlocking));
-  *out = ch;
   return 0;
 }
+}  // namespace
 
 extern "C" int gpbt_chain_destroy(gpbt_chain_t ch) {
   if (!ch) return 0;
@@ -684,11 +762,14 @@ int ensure_rows(gpbt_chain* ch, int64_t N) {
   if (N <= ch->cap_rows) return 0;
   const int64_t cap = std::max<int64_t>(N, 2 * ch->cap_rows);
   if (ch->z_mean) { cudaFree(ch->z_mean); cudaFree(ch->z_var); cudaFree(ch->extra); cudaFree(ch->skip); }
+  ch->z_mean = ch->z_var = ch->extra = nullptr; ch->skip = nullptr;
+  ch->ws_bytes -= ch->cap_rows * (2 * ch->Q * 8 + 9);
+  ch->cap_rows = 0;   // a failed allocation below leaves an empty, consistent workspace
   CU(cudaMalloc(&ch->z_mean, (size_t)cap * ch->Q * sizeof(double)));
   CU(cudaMalloc(&ch->z_var, (size_t)cap * ch->Q * sizeof(double)));
   CU(cudaMalloc(&ch->extra, (size_t)cap * sizeof(double)));
   CU(cudaMalloc(&ch->skip, (size_t)cap));
-  ch->ws_bytes += (cap - ch->cap_rows) * (2 * ch->Q * 8 + 9);
+  ch->ws_bytes += cap * (2 * ch->Q * 8 + 9);
   ch->cap_rows = cap;
   g_ws_generation++;
   return 0;
@@ -708,9 +789,12 @@ int64_t dense_chunk_rows(const gpbt_chain* ch, int64_t N) {
 int ensure_dense(gpbt_chain* ch, int64_t rows) {
   if (rows <= ch->cap_dense) return 0;
   if (ch->mean) { cudaFree(ch->mean); cudaFree(ch->cov); }
+  ch->mean = ch->cov = nullptr;
+  ch->ws_bytes -= ch->cap_dense * ((int64_t)ch->M * ch->M * 8 + (int64_t)ch->M * 8);
+  ch->cap_dense = 0;
   CU(cudaMalloc(&ch->mean, (size_t)rows * ch->M * sizeof(double)));
   CU(cudaMalloc(&ch->cov, (size_t)rows * ch->M * ch->M * sizeof(double)));
-  ch->ws_bytes += (rows - ch->cap_dense) * ((int64_t)ch->M * ch->M * 8 + (int64_t)ch->M * 8);
+  ch->ws_bytes += rows * ((int64_t)ch->M * ch->M * 8 + (int64_t)ch->M * 8);
   ch->cap_dense = rows;
   g_ws_generation++;
   return 0;
@@ -720,9 +804,12 @@ int ensure_io(gpbt_chain* ch, int64_t N) {
   if (N <= ch->cap_x) return 0;
   const int64_t cap = std::max<int64_t>(N, 2 * ch->cap_x);
   if (ch->x_dev) { cudaFree(ch->x_dev); cudaFree(ch->lp_dev); }
+  ch->x_dev = ch->lp_dev = nullptr;
+  ch->ws_bytes -= ch->cap_x * ((int64_t)ch->p * 8 + 8);
+  ch->cap_x = 0;
   CU(cudaMalloc(&ch->x_dev, (size_t)cap * ch->p * sizeof(double)));
   CU(cudaMalloc(&ch->lp_dev, (size_t)cap * sizeof(double)));
-  ch->ws_bytes += (cap - ch->cap_x) * ((int64_t)ch->p * 8 + 8);
+  ch->ws_bytes += cap * ((int64_t)ch->p * 8 + 8);
   ch->cap_x = cap;
   return 0;
 }
@@ -858,9 +945,12 @@ int log_posterior_impl(gpbt_chain_t ch, const double* X, double oob_value, doubl
     if (int r = ensure_rows(ch, chunk)) return r;
     if (chunk > ch->cap_diag) {
       if (ch->dmean) { cudaFree(ch->dmean); cudaFree(ch->dvar); }
+      ch->dmean = ch->dvar = nullptr;
+      ch->ws_bytes -= ch->cap_diag * (int64_t)ch->M * 16;
+      ch->cap_diag = 0;
       CU(cudaMalloc(&ch->dmean, (size_t)chunk * ch->M * sizeof(double)));
       CU(cudaMalloc(&ch->dvar, (size_t)chunk * ch->M * sizeof(double)));
-      ch->ws_bytes += (chunk - ch->cap_diag) * (int64_t)ch->M * 16;
+      ch->ws_bytes += chunk * (int64_t)ch->M * 16;
       ch->cap_diag = chunk;
       g_ws_generation++;
     }

@@ -9,6 +9,14 @@
 // W_j = L_j^-1 (inverted once on the host in FP64): V^T = K W_j^T, so the O(N n^2) term is a
 // triangular GEMM that runs on the FP64 tensor pipe (DMMA.8x8x4).
 //
+// KIND 2 is the surmise PCGP / PCSK predictor behind EmulatorBAND.predict (src/emulator_BAND.py:386-478;
+// the arithmetic lives in surmise 0.2.1 emulationmethods/PCGP.py, which is not part of the reference
+// tree -- restated from its published form, PARITY UNPINNED):
+//     r      = (1 - nug_j) * (a_j * prod_d (1 + s_d) * exp(-sum_d s_d) + b_j),  s_d = |x_d - theta_d| / exp(gamma_jd)
+//     z_mean = r @ pw_j,      z_var = sig2_j * | 1 - || r Vh_j ||^2 |
+// with c = (1 - nug) a, sn = (1 - nug) b and W_j = Vh_j^T, a DENSE n x n matrix: phase 2 then runs over
+// all k for every row block instead of k <= row.
+//
 // One CTA = one tile of TW walkers x one PC (TW = 16 with two CTAs resident per SM for large
 // batches, so one CTA's phase 1 overlaps the other's phase 2; 32 when two do not fit; 8 for small N).
 //   phase 1  the scaled design (rows X_train[k]/ell_j with alpha_j[k] appended) streams through
@@ -35,6 +43,7 @@ struct PcPredictParams {
   const double* __restrict__ c;      // [q]
   const double* __restrict__ sn;     // [q]
   const double* __restrict__ W;      // [q, n_pad, n_pad] lower-triangular inverse of L_j, zero padded
+  const double* __restrict__ sig2;   // [q]  KIND 2 only
   double* __restrict__ z_mean;       // [N, ldz]
   double* __restrict__ z_var;        // [N, ldz]
   int64_t ldz;
@@ -159,6 +168,7 @@ __global__ void __launch_bounds__(kPcThreads, TW == 16 ? 2 : 1) pc_predict_kerne
 
   // ---- phase 1: Kt and the mean ------------------------------------------------------------
   const double cj = prm.c[j];
+  const double offj = KIND == 2 ? prm.sn[j] : 0.0;
   {
     constexpr int LW = TW < 32 ? TW : 32;  // walkers covered by one warp pass
     constexpr int KPW = 32 / LW;           // k rows handled per warp pass (TW < 32)
@@ -183,7 +193,8 @@ __global__ void __launch_bounds__(kPcThreads, TW == 16 ? 2 : 1) pc_predict_kerne
         const double2* xr[UNR];
 #pragma unroll
         for (int u = 0; u < UNR; u++) {
-          acc[u] = acc1[u] = 0.0;
+          acc[u] = 0.0;
+          acc1[u] = KIND == 2 ? 1.0 : 0.0;   // KIND 2: acc = sum of s_d, acc1 = prod of (1 + s_d)
           xr[u] = reinterpret_cast<const double2*>(xc + (size_t)min(rb + u * KPW + ksub, rows_c - 1) * xrow);
         }
         if (P2 > 0) {
@@ -193,8 +204,15 @@ __global__ void __launch_bounds__(kPcThreads, TW == 16 ? 2 : 1) pc_predict_kerne
             for (int u = 0; u < UNR; u++) {
               const double2 tr = xr[u][d2];
               const double e0 = xreg[d2].x - tr.x, e1 = xreg[d2].y - tr.y;
-              acc[u] = fma(e0, e0, acc[u]);
-              acc1[u] = fma(e1, e1, acc1[u]);
+              if (KIND == 2) {
+                const double s0 = fabs(e0), s1 = fabs(e1);
+                acc[u] += s0 + s1;
+                acc1[u] = fma(acc1[u], s0, acc1[u]);
+                acc1[u] = fma(acc1[u], s1, acc1[u]);
+              } else {
+                acc[u] = fma(e0, e0, acc[u]);
+                acc1[u] = fma(e1, e1, acc1[u]);
+              }
             }
           }
         } else {
@@ -206,8 +224,15 @@ __global__ void __launch_bounds__(kPcThreads, TW == 16 ? 2 : 1) pc_predict_kerne
             for (int u = 0; u < UNR; u++) {
               const double2 tr = xr[u][d2];
               const double e0 = x.x - tr.x, e1 = x.y - tr.y;
-              acc[u] = fma(e0, e0, acc[u]);
-              acc1[u] = fma(e1, e1, acc1[u]);
+              if (KIND == 2) {
+                const double s0 = fabs(e0), s1 = fabs(e1);
+                acc[u] += s0 + s1;
+                acc1[u] = fma(acc1[u], s0, acc1[u]);
+                acc1[u] = fma(acc1[u], s1, acc1[u]);
+              } else {
+                acc[u] = fma(e0, e0, acc[u]);
+                acc1[u] = fma(e1, e1, acc1[u]);
+              }
             }
           }
         }
@@ -217,7 +242,9 @@ __global__ void __launch_bounds__(kPcThreads, TW == 16 ? 2 : 1) pc_predict_kerne
           const int kl = rb + u * KPW + ksub;
           const int k = c * kXsRows + kl;
           double kv;
-          if (KIND == 0) {
+          if (KIND == 2) {
+            kv = fma(cj, acc1[u] * exp_neg(-acc[u], etab), offj);
+          } else if (KIND == 0) {
             kv = cj * exp_neg(-0.5 * d2sum, etab);
           } else {
             const double r = sqrt(d2sum) * 1.7320508075688772;  // sqrt(3) rounded as np.sqrt(3)
@@ -269,6 +296,17 @@ __global__ void __launch_bounds__(kPcThreads, TW == 16 ? 2 : 1) pc_predict_kerne
       // buffers (no copies, loads run one full chunk ahead of their use)
       double a0[4][4], a1[4][4];
       load_a<0>(a0, Wrow, n_pad, 0);
+      if (KIND == 2) {
+        // dense W: every k chunk contributes to every row block
+        const int nch = n_pad / kKChunk;
+#pragma unroll 1
+        for (int cp = 0; 2 * cp < nch; cp++) {
+          load_a<0>(a1, Wrow, n_pad, 2 * cp + 1);
+          mma_chunk<TW, 0>(acc, a0, Kt, (2 * cp) * kKChunk, g, t);
+          load_a<0>(a0, Wrow, n_pad, min(2 * cp + 2, nch - 1));   // (last pass: a harmless reload)
+          mma_chunk<TW, 0>(acc, a1, Kt, (2 * cp + 1) * kKChunk, g, t);
+        }
+      } else {
 #pragma unroll 1
       for (int cp = 0; cp < rb; cp++) {
         load_a<0>(a1, Wrow, n_pad, 2 * cp + 1);
@@ -281,6 +319,7 @@ __global__ void __launch_bounds__(kPcThreads, TW == 16 ? 2 : 1) pc_predict_kerne
       load_a<2>(a1, Wrow, n_pad, 2 * rb + 1);
       mma_chunk<TW, 0>(acc, a0, Kt, (2 * rb) * kKChunk, g, t);
       mma_chunk<TW, 2>(acc, a1, Kt, (2 * rb + 1) * kKChunk, g, t);
+      }
 #pragma unroll
       for (int mb = 0; mb < 4; mb++)
 #pragma unroll
@@ -311,7 +350,8 @@ __global__ void __launch_bounds__(kPcThreads, TW == 16 ? 2 : 1) pc_predict_kerne
       s2 += red_ssq[wp * TW + tid];
     }
     double var = (cj + prm.sn[j]) - s2;  // diag(kernel_(X)) = c + sn; no clamping (return_cov branch)
-    if (prm.extra != nullptr) {
+    if (KIND == 2) var = prm.sig2[j] * fabs(1.0 - s2);   // extra_std is accepted and ignored by EmulatorBAND
+    if (KIND != 2 && prm.extra != nullptr) {
       const double e = prm.extra[w0 + tid];
       var += e * e;
     }

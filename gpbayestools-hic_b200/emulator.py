@@ -230,6 +230,39 @@ class Emulator:
         the nsamples x nobs x nobs array -- for posterior-predictive and sensitivity sweeps."""
         return self._dev().predict_diag(X, extra_std=extra_std)
 
+    # ---- validation helpers (callers of predict; src/emulator.py:418-421, 636-726) ----------------
+    def getAvgTrainingDataRelError(self):
+        """mean over the design of (statistical error / value) per observable"""
+        return np.mean(np.nan_to_num(self.model_data_err / self.model_data), axis=0)
+
+    def _hold_out(self, nTestPoints, test_on_training_points):
+        """Train without the last nTestPoints design points, predict either those (validation) or the
+        points trained on (closure); returns (prediction, its std, data, data error), each
+        [points, nobs], back on the linear scale when the emulator works with log observables.
+        The std comes from predict_diag: same numbers as sqrt(diag(cov)) without the covariances."""
+        log.info("Validating GP emulator ...")
+        train = np.ones(self.nev, dtype=bool)
+        train[self.nev - nTestPoints:] = False
+        self.trainEmulator(list(train))
+        rows = train if test_on_training_points else ~train
+        pred, var = self.predict_diag(self.design_points_org_[rows, :])
+        std = np.sqrt(var)
+        if self.logTrafo_ and not self.exp_and_cov_diagonal_:
+            pred, std = np.exp(pred), std * np.exp(pred)
+        data, err = self.model_data[rows, :], self.model_data_err[rows, :]
+        if self.logTrafo_:
+            data, err = np.exp(data), err * np.exp(data)
+        shape = (-1, self.nobs)
+        return pred.reshape(shape), std.reshape(shape), data.reshape(shape), err.reshape(shape)
+
+    def testEmulatorErrors(self, nTestPoints=1):
+        """Train on all but the last nTestPoints design points and predict those."""
+        return self._hold_out(nTestPoints, test_on_training_points=False)
+
+    def testEmulatorErrorsWithTrainingPoints(self, nTestPoints=1):
+        """Same training, but the predictions are made at the points trained on."""
+        return self._hold_out(nTestPoints, test_on_training_points=True)
+
     # ---- pickling: device handles never travel -------------------------------------------------
     def __getstate__(self):
         d = dict(self.__dict__)

@@ -123,7 +123,7 @@ class ParamTrafo:
 
 @dataclass
 class EmulatorState:
-    kind: str                 # "RBF" | "Matern"
+    kind: str                 # "RBF" | "Matern" | "PCGP" (surmise PCGP / PCSK, see from_pcgp_fitinfo)
     Xtr: np.ndarray           # [n, p]
     ell: np.ndarray           # [q, p]
     c: np.ndarray             # [q]
@@ -138,6 +138,8 @@ class EmulatorState:
     exp_diag: bool = False
     L: Optional[np.ndarray] = None        # [q, n, n] kept only for oracle comparisons
     trafo: Optional[ParamTrafo] = None    # parameterTrafoPCA pre-transform (then p counts transformed columns)
+    sig2: Optional[np.ndarray] = None     # [q]  PCGP only; there c / sn hold (1-nug)a / (1-nug)b, alpha = pw, Linv = Vh^T
+    pcgp: Optional[dict] = None           # PCGP only: hypcov [q,p+1], nug [q], Vh [q,n,n] (oracle comparisons)
     _handle: Optional[C.c_void_p] = field(default=None, repr=False, compare=False)
 
     # ---- shapes ---------------------------------------------------------------------------
@@ -176,6 +178,10 @@ class EmulatorState:
         `exp_and_cov_diagonal_` -- i.e. a dill-loaded reference `src.emulator.Emulator` or this
         package's `Emulator`."""
         trafo = ParamTrafo.from_trained(emu) if getattr(emu, "parameterTrafoPCA_", False) else None
+        if not hasattr(emu, "gps") and hasattr(emu, "emu"):
+            # EmulatorBAND: the trained object is a surmise emulator (src/emulator_BAND.py:270-292)
+            info = emu.emu if isinstance(emu.emu, dict) else emu.emu._info
+            return cls.from_pcgp_fitinfo(info, exp_diag=bool(getattr(emu, "exp_and_cov_diagonal_", False)), trafo=trafo)
         gps = emu.gps
         hyp = [_kernel_kind_and_hypers(g.kernel_) for g in gps]
         kinds = {h[0] for h in hyp}
@@ -195,9 +201,43 @@ class EmulatorState:
             L=np.stack([g.L_ for g in gps]), no_pca=no_pca,
             exp_diag=bool(getattr(emu, "exp_and_cov_diagonal_", False)), keep_L=keep_L, trafo=trafo)
 
+    @classmethod
+    def from_pcgp_fitinfo(cls, info, exp_diag=False, extravar_in_cov=False, trafo=None):
+        """From the fit information of a surmise PCGP / PCSK emulator (`emulator._info` of the object
+        the reference keeps in EmulatorBAND.emu, src/emulator_BAND.py:270-292):
+            theta [n,p], pct [m,q], scale [m], offset [m], extravar [m],
+            emulist[k] = {hypcov [p+1], hypind, nug, Vh [n,n], pw [n], sig2}
+        PCs that share hyper-parameters (hypind) are expanded: the kernels evaluate every PC anyway.
+        covx() of surmise 0.2.1 is pct diag(predvar) pct^T without extravar as far as its published
+        source shows; `extravar_in_cov=True` adds diag(extravar).  PARITY UNPINNED (no surmise here)."""
+        theta = _f64(info["theta"])
+        emul = info["emulist"]
+        q, (n, p) = len(emul), theta.shape
+        hyp = np.stack([_f64(emul[int(e.get("hypind", k))]["hypcov"]).reshape(p + 1) for k, e in enumerate(emul)])
+        nug = np.array([float(np.squeeze(e["nug"])) for e in emul])
+        g = np.exp(hyp[:, -1])
+        pct = _f64(info["pct"] if "pct" in info else info["pcti"]).reshape(-1, q)
+        scale = _f64(info["scale"]).reshape(-1)
+        m = scale.shape[0]
+        Vh = np.stack([_f64(e["Vh"]).reshape(n, n) for e in emul])
+        extra = np.diag(_f64(info["extravar"]).reshape(m)) if extravar_in_cov else np.zeros((m, m))
+        return cls(kind="PCGP", Xtr=theta, ell=_f64(np.exp(hyp[:, :-1])), c=_f64((1.0 - nug) / (1.0 + g)),
+                   sn=_f64((1.0 - nug) * g / (1.0 + g)),
+                   alpha=np.stack([_f64(e["pw"]).reshape(n) for e in emul]),
+                   Linv=_f64(np.swapaxes(Vh, 1, 2)), mu=_f64(info["offset"]).reshape(m), scale=np.ones(m),
+                   A=_f64((pct * scale[:, None]).T), Ctrunc=_f64(extra), no_pca=False, exp_diag=bool(exp_diag),
+                   L=None, trafo=trafo, sig2=_f64([float(np.squeeze(e["sig2"])) for e in emul]),
+                   pcgp=dict(hypcov=hyp, nug=nug, Vh=Vh))
+
     # ---- views ----------------------------------------------------------------------------
     def oracle_dict(self):
         """The layout oracle/gp_oracle.py works on (tests only)."""
+        if self.kind == "PCGP":
+            d = dict(kind="PCGP", Xtr=self.Xtr, pw=self.alpha, sig2=self.sig2, no_pca=False, exp_diag=self.exp_diag,
+                     mu=self.mu, scale=self.scale, A=self.A, Ctrunc=self.Ctrunc, **self.pcgp)
+            if self.trafo is not None:
+                d["trafo"] = dict(p_in=self.trafo.p_in, groups=self.trafo.groups)
+            return d
         if self.L is None:
             raise ValueError("state was built with keep_L=False")
         d = dict(kind=self.kind, Xtr=self.Xtr, ell=self.ell, c=self.c, sn=self.sn, alpha=self.alpha,
@@ -219,12 +259,18 @@ class EmulatorState:
             from . import _lib
             h = C.c_void_p()
             flags = (_lib.FLAG_NO_PCA if self.no_pca else 0) | (_lib.FLAG_EXP_DIAG if self.exp_diag else 0)
-            kind = {"RBF": _lib.KERNEL_RBF, "Matern": _lib.KERNEL_MATERN32}[self.kind]
             hp = _lib.host_ptr
-            _lib.check(_lib.lib.gpbt_emulator_create(
-                C.byref(h), self.p, self.n, self.q, self.m, kind, flags, hp(self.Xtr), hp(self.ell),
-                hp(self.c), hp(self.sn), hp(self.alpha), hp(self.Linv), hp(self.A), hp(self.mu),
-                hp(self.scale), hp(self.Ctrunc)))
+            if self.kind == "PCGP":
+                _lib.check(_lib.lib.gpbt_emulator_create_pcgp(
+                    C.byref(h), self.p, self.n, self.q, self.m, flags, hp(self.Xtr), hp(self.ell), hp(self.c),
+                    hp(self.sn), hp(self.sig2), hp(self.alpha), hp(self.Linv), hp(self.A), hp(self.mu),
+                    hp(self.Ctrunc)))
+            else:
+                kind = {"RBF": _lib.KERNEL_RBF, "Matern": _lib.KERNEL_MATERN32}[self.kind]
+                _lib.check(_lib.lib.gpbt_emulator_create(
+                    C.byref(h), self.p, self.n, self.q, self.m, kind, flags, hp(self.Xtr), hp(self.ell),
+                    hp(self.c), hp(self.sn), hp(self.alpha), hp(self.Linv), hp(self.A), hp(self.mu),
+                    hp(self.scale), hp(self.Ctrunc)))
             if self.trafo is not None:
                 t = self.trafo
                 ng = len(t.groups)

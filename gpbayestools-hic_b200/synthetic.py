@@ -142,3 +142,41 @@ def untrained_state_arrays(p, n, m, q, kind="RBF", seed=17, ell_range=(0.8, 4.0)
     alpha = np.stack([cho_solve((L[j], True), Z[:, j]) for j in range(q)])
     return dict(kind=kind, Xtr=Xtr, ell=ell, c=cs, sn=sns, alpha=alpha, mu=mu, scale=scale, A=A,
                 Ctrunc=Ctrunc, L=L)
+
+
+def pcgp_fitinfo(p, n, m, q, seed=23, nug=1e-4, shared_hyper=True):
+    """A surmise-PCGP-shaped fit (`emulator._info`) built with NumPy on the synthetic simulator, for
+    tests and benchmarks of the EmulatorBAND path -- surmise itself is not installed here, so the
+    hyper-parameters are drawn, not optimised: standardised outputs -> SVD principal components ->
+    per PC the separable-Matern correlation R, its eigen-factor Vh = V / sqrt(W), pw = R^-1 g and
+    sig2 = g . pw / n.  Pairs of PCs share hyper-parameters (hypind) as surmise's fit does."""
+    rng = np.random.default_rng(seed)
+    lo, hi = box(p)
+    theta = design(p, n, seed=seed)
+    W1 = rng.normal(0, 1 / np.sqrt(p), (p, 24))
+    W2 = rng.normal(0, 1 / np.sqrt(24), (24, m))
+    U = (theta - lo) / (hi - lo)
+    F = 5 + np.tanh(2 * U @ W1) @ W2 + 0.5 * np.sin(3 * U[:, :1]) * np.linspace(0, 1, m) + 0.01 * rng.normal(size=(n, m))
+    offset, scale = F.mean(0), F.std(0)
+    Z = (F - offset) / scale
+    _, S, Vt = np.linalg.svd(Z, full_matrices=False)
+    pct = (Vt[:q].T * S[:q] / np.sqrt(n))                       # [m, q]
+    G = Z @ np.linalg.pinv(pct).T                               # PC scores [n, q]
+    emulist = []
+    for k in range(q):
+        hypind = k - (k % 2) if shared_hyper else k
+        if hypind == k:
+            hyp = np.concatenate((np.log((hi - lo) * rng.uniform(0.6, 2.5, p)), [rng.uniform(-4.0, -2.0)]))
+        else:
+            hyp = emulist[hypind]["hypcov"]
+        w = 1.0 / (1.0 + np.exp(hyp[-1]))
+        S_ = np.abs(theta[:, None, :] - theta[None, :, :]) / np.exp(hyp[:-1])
+        R = w * np.prod(1 + S_, axis=2) * np.exp(-S_.sum(axis=2)) + (1 - w)
+        Rn = (1 - nug) * R + nug * np.eye(n)
+        ev, V = np.linalg.eigh(Rn)
+        Vh = V / np.sqrt(np.abs(ev))
+        pw = Vh @ (Vh.T @ G[:, k])
+        emulist.append(dict(hypcov=hyp, hypind=hypind, nug=nug, Vh=Vh, pw=pw, sig2=float(G[:, k] @ pw / n)))
+    resid = Z - G @ pct.T
+    return dict(theta=theta, pct=pct, pcti=pct, scale=scale, offset=offset,
+                extravar=np.mean(resid ** 2, axis=0) * scale ** 2, emulist=emulist, method="PCGP")

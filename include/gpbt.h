@@ -35,7 +35,7 @@ extern "C" {
 typedef struct gpbt_emulator* gpbt_emulator_t; /* device-resident trained state of one emulator */
 typedef struct gpbt_chain* gpbt_chain_t;       /* emulators + experimental data + workspaces    */
 
-enum { GPBT_KERNEL_RBF = 0, GPBT_KERNEL_MATERN32 = 1 };
+enum { GPBT_KERNEL_RBF = 0, GPBT_KERNEL_MATERN32 = 1, GPBT_KERNEL_PCGP = 2 /* gpbt_emulator_create_pcgp only */ };
 enum { GPBT_FLAG_NO_PCA = 1, GPBT_FLAG_EXP_DIAG = 2 };
 enum { GPBT_PATH_AUTO = 0, GPBT_PATH_DENSE = 1, GPBT_PATH_LOWRANK = 2, GPBT_PATH_DIAG = 3 };
 enum {
@@ -63,6 +63,28 @@ int gpbt_emulator_create(gpbt_emulator_t* out, int p, int n, int q, int m, int k
                          const double* Linv_host, const double* A_host, const double* mu_host,
                          const double* scale_host, const double* Ctrunc_host);
 int gpbt_emulator_destroy(gpbt_emulator_t emu);
+
+/* surmise PCGP / PCSK emulator state, the object behind EmulatorBAND.predict
+ * (src/emulator_BAND.py:270-292 fit, :386-478 predict = self.emu.predict(x, theta).mean() / .covx()).
+ * The arithmetic is inside surmise 0.2.1 (requirements.txt), which is NOT part of the reference tree
+ * and not installed in the build image: this entry point follows the published form of
+ * emulationmethods/PCGP.py `predict` and its parity against surmise itself is UNPINNED.
+ *   theta [n,p]   fitinfo['theta']                  ell [q,p]  exp(hypcov[:-1]) of each PC's GP
+ *   amp   [q]     (1 - nug) / (1 + exp(hypcov[-1])) off [q]    (1 - nug) exp(hypcov[-1]) / (1 + exp(hypcov[-1]))
+ *   sig2  [q]     emulist[k]['sig2']                pw  [q,n]  emulist[k]['pw']
+ *   VhT   [q,n,n] transpose of emulist[k]['Vh']     A   [q,m]  (pct * scale[:,None]).T
+ *   offset [m]    fitinfo['offset']                 extra_cov [m,m] constant added to every covariance
+ *                                                   (zeros for covx(); diag(extravar) for the variant)
+ * Per walker:  r = amp * prod_d(1 + s_d) exp(-sum_d s_d) + off,  s_d = |x_d - theta_d| / ell_d;
+ *   z_mean = r . pw,  z_var = sig2 |1 - |r Vh|^2|;  mean = z_mean A + offset,
+ *   cov = A^T diag(z_var) A + extra_cov.  GPBT_FLAG_EXP_DIAG as for gpbt_emulator_create.
+ * extra_std passed to gpbt_pc_predict is ignored, as EmulatorBAND.predict ignores it.
+ * All pointers are HOST pointers.                                                             */
+int gpbt_emulator_create_pcgp(gpbt_emulator_t* out, int p, int n, int q, int m, int flags,
+                              const double* theta_host, const double* ell_host, const double* amp_host,
+                              const double* off_host, const double* sig2_host, const double* pw_host,
+                              const double* VhT_host, const double* A_host, const double* offset_host,
+                              const double* extra_cov_host);
 
 /* Optional "parameterTrafoPCA" pre-transform in front of kernel (a) (src/emulator.py:492-551,
  * src/emulator_BAND.py:393-452): walkers arrive with p_in model parameters; the columns listed in

@@ -20,11 +20,18 @@ It is a plain NumPy/SciPy restatement of what the reference computes between
   src/mcmc.py Chain.log_likelihood     (:188-222)        log_likelihood
   src/mcmc.py Chain.log_posterior      (:261-299)        log_posterior
 
+  src/emulator_BAND.py EmulatorBAND.predict (:386-478)  pcgp_pc_predict + emulator_predict (kind "PCGP")
+
 Parity pin: tests/test_oracle_golden.py checks every function here against golden vectors that
 tests/golden/make_golden.py produced by importing and running the UNMODIFIED reference
-(/root/reference/src, scikit-learn 1.9.0) in the build container.  The surmise (EmulatorBAND)
-path has no pin: surmise 0.2.1 is not installed and its source is not in the reference tree
-("parity unpinned" for that path).
+(/root/reference/src, scikit-learn 1.9.0) in the build container.
+
+PARITY UNPINNED for the surmise (EmulatorBAND) path: `self.emu.predict(x, theta).mean() / .covx()` is
+computed inside surmise 0.2.1 (requirements.txt:1), which is neither installed here nor vendored in
+the reference tree, so no golden vector can be generated.  pcgp_covmat / pcgp_pc_predict restate the
+published algorithm of surmise's emulationmethods/PCGP.py (`__covmat`, `predict`; PCSK's predict has
+the same form) from its documentation and from SURVEY 8c; they pin the CUDA kernels to that
+restatement, not to surmise itself.
 
 An emulator "state" is a dict of float64 arrays (the trained quantities the reference keeps on
 its sklearn objects):
@@ -111,11 +118,42 @@ def param_trafo(trafo, X):
     return np.concatenate(cols, axis=1)
 
 
+def pcgp_covmat(x1, x2, gammav):
+    """surmise PCGP `__covmat`: separable Matern-3/2 in |x1_d - x2_d| / exp(gamma_d) mixed with a
+    constant, weights 1/(1+e^g) and e^g/(1+e^g) for g = gammav[-1].  [UNPINNED restatement]"""
+    x1, x2 = np.atleast_2d(x1), np.atleast_2d(x2)
+    V = np.zeros((x1.shape[0], x2.shape[0]))
+    R = np.full((x1.shape[0], x2.shape[0]), 1.0 / (1.0 + np.exp(gammav[-1])))
+    for k in range(len(gammav) - 1):
+        S = np.abs(np.subtract.outer(x1[:, k], x2[:, k]) / np.exp(gammav[k]))
+        R *= (1.0 + S)
+        V -= S
+    R *= np.exp(V)
+    R += np.exp(gammav[-1]) / (1.0 + np.exp(gammav[-1]))
+    return R
+
+
+def pcgp_pc_predict(state, theta):
+    """surmise PCGP `predict`, PC space: predvec_k = r pw_k, predvar_k = sig2_k |1 - |r Vh_k|^2| with
+    r = (1 - nug_k) covmat(theta, theta_train, hypcov_k).  [UNPINNED restatement]"""
+    q = state["pw"].shape[0]
+    zm, zv = np.empty((theta.shape[0], q)), np.empty((theta.shape[0], q))
+    for k in range(q):
+        r = (1.0 - state["nug"][k]) * pcgp_covmat(theta, state["Xtr"], state["hypcov"][k])
+        rVh = r @ state["Vh"][k]
+        zm[:, k] = r @ state["pw"][k]
+        zv[:, k] = state["sig2"][k] * np.abs(1.0 - np.sum(rVh ** 2, axis=1))
+    return zm, zv
+
+
 def pc_predict(state, X, extra_std=None):
-    """z_mean[N,q], z_var[N,q] for all GPs; z_var includes extra_std**2 (src/emulator.py:573-579)."""
+    """z_mean[N,q], z_var[N,q] for all GPs; z_var includes extra_std**2 (src/emulator.py:573-579).
+    For a PCGP state extra_std is ignored, as EmulatorBAND.predict ignores it (src/emulator_BAND.py:386)."""
     X = np.asarray(X, dtype=np.float64)
     if state.get("trafo") is not None:
         X = param_trafo(state["trafo"], X)
+    if state["kind"] == "PCGP":
+        return pcgp_pc_predict(state, X)
     q = state["alpha"].shape[0]
     zm = np.empty((X.shape[0], q))
     zv = np.empty((X.shape[0], q))

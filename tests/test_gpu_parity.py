@@ -178,6 +178,32 @@ def test_chain_class_drop_in(tmp_path):
     assert np.max(np.abs(ch.log_likelihood_point_by_point(X[:7]) - lp[:7])[fin[:7]]) <= 1e-10
 
 
+@pytest.mark.parametrize("log_trafo", [False, True])
+def test_emulator_validation_helpers(tmp_path, log_trafo):
+    """testEmulatorErrors / testEmulatorErrorsWithTrainingPoints (src/emulator.py:636-726): hold the last
+    design points out, retrain, predict -- against the oracle evaluated on the retrained state."""
+    from gpbt_b200 import synthetic
+    from gpbt_b200.emulator import Emulator
+    paths = synthetic.write_fixture(str(tmp_path), p=4, n=50, m=12)
+    emu = Emulator(training_set_path=paths["train"], parameter_file=paths["par"], npc=5, logTrafo=log_trafo)
+    pred, err, data, derr = emu.testEmulatorErrors(nTestPoints=4)
+    assert pred.shape == err.shape == data.shape == derr.shape == (4, 12)
+    st = emu.state.oracle_dict()
+    assert st["Xtr"].shape[0] == emu.nev - 4
+    Xv = emu.design_points_org_[-4:]
+    omean, ocov = orc.emulator_predict(st, Xv, True, np.zeros(4))
+    ostd = np.sqrt(np.array([c.diagonal() for c in ocov]))
+    if log_trafo:
+        omean, ostd = np.exp(omean), ostd * np.exp(omean)
+    assert rel_err(pred, omean) <= REL and rel_err(err, ostd) <= 1e-8
+    want = np.exp(emu.model_data[-4:]) if log_trafo else emu.model_data[-4:]
+    assert np.array_equal(data, want)
+    assert np.median(np.abs(pred - data) / np.abs(data)) < 0.05        # it does emulate the held-out points
+    p2, e2, d2, de2 = emu.testEmulatorErrorsWithTrainingPoints(nTestPoints=4)
+    assert p2.shape == (emu.nev - 4, 12) and np.median(np.abs(p2 - d2) / np.abs(d2)) < 0.02
+    assert emu.getAvgTrainingDataRelError().shape == (12,)
+
+
 def test_invariances():
     """Size-independent properties: permutation equivariance over walkers, chunking invariance,
     tile-width invariance (N small -> narrow tiles, N large -> wide tiles give the same numbers)."""
