@@ -147,3 +147,33 @@ emit({"config": "C3 shape (p15,n1000,m300,q20), RBF GP emulator (surmise PCSK it
       "N_per_call": 8192, "evals_per_s": rate, "ms_per_call": dt * 1e3,
       "max_abs_diff_lowrank_vs_dense_256_rows": float(np.max(np.abs(lp[:256][fin] - dense[fin]))),
       "note": "parity of this shape against the oracle: tests/test_gpu_parity.py::test_n1000_shape"})
+ch3.release()
+
+# ---- config 3 proper: surmise-PCGP-shaped emulator (kernel kind 2: separable Matern + constant, dense Vh) ----
+info = synthetic.pcgp_fitinfo(15, 1000, 300, 20)
+stb = EmulatorState.from_pcgp_fitinfo(info)
+yb = info["offset"] + 0.3 * info["scale"]
+chb = DeviceChain([stb], lo, hi, yb, np.diag((0.03 * np.abs(yb)) ** 2))
+rate, dt, lp = host_rate(chb, X, 5)
+dense = chb.log_target(X[:256], -np.inf, path="dense")
+fin = np.isfinite(dense)
+deb = DeviceEmulator(stb)
+Xd3 = torch.from_numpy(X).cuda()
+deb.pc_predict_device(Xd3)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(5):
+    deb.pc_predict_device(Xd3)
+e1.record()
+torch.cuda.synchronize()
+ka = e0.elapsed_time(e1) * 1e-3 / 5
+# per evaluation: q n (4 p + 6) for the kernel row (|d|, sum, product per dimension) + 2 q n for the mean
+# + 2 q n^2 for r Vh (dense) + 2 q n for the squares
+fl = 20 * 1000 * (4 * 15 + 6) + 2 * 20 * 1000 + 2 * 20 * 1000 * 1000 + 2 * 20 * 1000
+emit({"config": "C3 (p15,n1000,m300,q20), surmise-PCGP-shaped emulator (EmulatorBAND path; parity unpinned: surmise absent)",
+      "N_per_call": 8192, "evals_per_s": rate, "ms_per_call": dt * 1e3,
+      "kernel_a_ms": ka * 1e3, "kernel_a_TFLOPs": fl * 8192 / ka / 1e12, "algorithmic_flops_per_eval": fl,
+      "max_abs_diff_lowrank_vs_dense_256_rows": float(np.max(np.abs(lp[:256][fin] - dense[fin]))),
+      "note": "values against the restatement: tests/test_gpu_band.py"})
+chb.release()
