@@ -20,7 +20,7 @@ SYMBOLS = [
     "gpbt_chain_destroy", "gpbt_chain_predict", "gpbt_log_posterior", "gpbt_log_posterior_scatter",
     "gpbt_log_posterior_host",
     "gpbt_chain_workspace_bytes", "gpbt_launch_count", "gpbt_debug_exp_neg",
-    "gpbt_ensemble_create", "gpbt_ensemble_destroy", "gpbt_ensemble_set_state", "gpbt_ensemble_get_state",
+    "gpbt_host_temp_exchange", "gpbt_ensemble_create", "gpbt_ensemble_destroy", "gpbt_ensemble_set_state", "gpbt_ensemble_get_state",
     "gpbt_ensemble_run", "gpbt_ensemble_steps", "gpbt_ensemble_reserve", "gpbt_ensemble_read", "gpbt_ensemble_reset",
 ]
 
@@ -57,6 +57,7 @@ def _load():
     lib.gpbt_debug_exp_neg.argtypes = [dp, dp, i64, vp]
     lib.gpbt_chain_workspace_bytes.argtypes = [vp]
     lib.gpbt_chain_workspace_bytes.restype = i64
+    lib.gpbt_host_temp_exchange.argtypes = [dp, dp, i64, dp, dp, i64, dp]
     lib.gpbt_ensemble_create.argtypes = [C.POINTER(vp), vp, i32, dbl, i32, C.c_uint64]
     lib.gpbt_ensemble_destroy.argtypes = [vp]
     lib.gpbt_ensemble_set_state.argtypes = [vp, dp, dp]

@@ -40,7 +40,27 @@ def temperature_ladder(numtemps, numchain, maxtemp):
 
 def temp_exchange(lpostf, temps, iters=1):
     """Random adjacent swaps along the ladder; returns the new ordering of the chains.
-    lpostf [n] or [n, 1] untempered log-posteriors, temps likewise (src/mcmc.py:679-693)."""
+    lpostf [n] or [n, 1] untempered log-posteriors, temps likewise (src/mcmc.py:679-693).
+
+    Per sweep the reference draws n slots, then one uniform per slot as it walks through them; n
+    uniforms drawn in one call are the same numbers in the same order, so the draws are made up
+    front and the (inherently sequential) swap loop runs in the library's host helper."""
+    from . import _lib
+    n = lpostf.shape[0]
+    lp = np.ascontiguousarray(lpostf, dtype=np.float64).reshape(n)
+    tt = np.ascontiguousarray(temps, dtype=np.float64).reshape(n)
+    order = np.arange(0, n, dtype=np.int64)
+    slots = np.arange(1, n)
+    for _ in range(iters):
+        picks = np.ascontiguousarray(np.random.choice(slots, n), dtype=np.int64)
+        log_u = np.log(np.random.uniform(size=n))
+        _lib.check(_lib.lib.gpbt_host_temp_exchange(_lib.host_ptr(lp), _lib.host_ptr(tt), n, _lib.host_ptr(picks),
+                                                    _lib.host_ptr(log_u), n, _lib.host_ptr(order)))
+    return order
+
+
+def temp_exchange_python(lpostf, temps, iters=1):
+    """The same sweep as a plain Python loop (kept for the tests: draw-for-draw the reference's)."""
     n = lpostf.shape[0]
     order = np.arange(0, n)
     slots = np.arange(1, n)

@@ -226,6 +226,15 @@ int gpbt_ensemble_read(gpbt_ensemble_t ens, int64_t first, int64_t n, double* ch
 /* forget the history and the acceptance counts; the walkers stay where they are              */
 int gpbt_ensemble_reset(gpbt_ensemble_t ens);
 
+/* HOST helper (no GPU work): one sweep of Chain.tempexchange (src/mcmc.py:679-693) over n_picks
+ * caller-drawn picks rt in [1, n) and log-uniform draws; swaps order[rt-1], order[rt] where
+ * (lp[order[rt]] - lp[order[rt-1]]) * (1/temps[rt-1] - 1/temps[rt]) > log_u[i].  order is updated
+ * in place.  The swaps depend on each other, so the loop is sequential; it is here because in
+ * Python it dominates a PTLMC iteration at thousands of chains.                                 */
+int gpbt_host_temp_exchange(const double* lp_host, const double* temps_host, int64_t n,
+                            const int64_t* picks_host, const double* log_u_host, int64_t n_picks,
+                            int64_t* order_host);
+
 /* bytes of device workspace the chain currently holds (grows with the largest N seen)        */
 int64_t gpbt_chain_workspace_bytes(gpbt_chain_t chain);
 

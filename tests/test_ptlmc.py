@@ -31,6 +31,18 @@ def test_temp_exchange_matches_reference(toy):
     order = ptlmc.temp_exchange(g["ex_lp"], g["ex_temps"], iters=4)
     np.testing.assert_array_equal(order, g["ex_order"])
     assert sorted(order) == list(range(9))
+    np.random.seed(100)
+    np.testing.assert_array_equal(ptlmc.temp_exchange_python(g["ex_lp"], g["ex_temps"], iters=4), g["ex_order"])
+    # a ladder long enough for many dependent swaps: helper and Python loop agree draw for draw
+    rng = np.random.default_rng(5)
+    lp, temps = rng.normal(size=(700, 1)) * 40, ptlmc.temperature_ladder(500, 200, 50.0)
+    np.random.seed(8)
+    a = ptlmc.temp_exchange(lp, temps, iters=5)
+    state = np.random.get_state()[1][:4].copy()
+    np.random.seed(8)
+    b = ptlmc.temp_exchange_python(lp, temps, iters=5)
+    np.testing.assert_array_equal(a, b)
+    assert np.array_equal(state, np.random.get_state()[1][:4]) and (a != np.arange(700)).sum() > 100
 
 
 def test_chain_matches_reference_without_gradient(toy):

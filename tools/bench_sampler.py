@@ -101,3 +101,45 @@ states2 = [EmulatorState.from_arrays(s["kind"], s["Xtr"], s["ell"], s["c"], s["s
 dc = DeviceChain(states2, g2["lo"], g2["hi"], g2["y_exp"].reshape(-1), g2["cov_exp"])
 run("C2 (p17,n500,m300,q20)", dc, g2["lo"], g2["hi"], 8192, 300, 100)
 dc.release()
+
+# ---- config 3: one PTLMC iteration at 8192 chains on the surmise-PCGP-shaped emulator -------------
+# (the move of gpbt_b200.ptlmc.sampler_ptlmc without its start-up: proposal, one GPU call, Metropolis,
+# five exchange sweeps; the pre-optimiser is N = 1 L-BFGS-B calls per chain and is not timed here)
+from gpbt_b200 import ptlmc, synthetic  # noqa: E402
+
+info = synthetic.pcgp_fitinfo(15, 1000, 300, 20)
+lo3, hi3 = synthetic.box(15)
+y3 = info["offset"] + 0.3 * info["scale"]
+dc = DeviceChain([EmulatorState.from_pcgp_fitinfo(info)], lo3, hi3, y3, np.diag((0.03 * np.abs(y3)) ** 2))
+n_all = 8192
+temps = ptlmc.temperature_ladder(n_all - 1024, 1024, 100.0)
+theta = start(lo3, hi3, n_all)
+f = dc.log_target(theta, -np.inf).reshape(-1, 1) / temps
+root = np.diag(0.02 * (hi3 - lo3))
+t_call = t_np = t_ex = t_ex_py = 0.0
+iters = 10
+np.random.seed(0)
+for k in range(iters):
+    t0 = time.perf_counter()
+    prop = theta + np.sqrt(2) * temps ** (1 / 3) * (np.random.normal(0, 1, theta.shape) @ root)
+    t1 = time.perf_counter()
+    fp = dc.log_target(prop, -np.inf).reshape(-1, 1) / temps
+    t2 = time.perf_counter()
+    take = np.where(np.log(np.random.uniform(size=n_all)) < np.squeeze(fp - f))[0]
+    theta[take], f[take] = prop[take], fp[take]
+    t3 = time.perf_counter()
+    flat = f * temps
+    order = ptlmc.temp_exchange(flat, temps, iters=5)
+    t4 = time.perf_counter()
+    if k < 2:
+        ptlmc.temp_exchange_python(flat, temps, iters=5)
+        t_ex_py += time.perf_counter() - t4
+    f, theta = flat[order] / temps, theta[order]
+    t_np += (t1 - t0) + (t3 - t2)
+    t_call += t2 - t1
+    t_ex += t4 - t3
+emit({"config": "C3 (p15,n1000,m300,q20, surmise-PCGP-shaped), PTLMC iteration at 8192 chains", "chains": n_all,
+      "ms_gpu_call": 1e3 * t_call / iters, "ms_numpy_proposal_accept": 1e3 * t_np / iters,
+      "ms_exchange_host_helper": 1e3 * t_ex / iters, "ms_exchange_python_loop": 1e3 * t_ex_py / 2,
+      "iterations_per_s": iters / (t_call + t_np + t_ex)})
+dc.release()
