@@ -226,3 +226,32 @@ def test_run_mcmc_ptlmc_on_gpu_posterior(tmp_path):
     assert np.all(np.isfinite(lp)) and np.max(np.abs(lp[:10] - want)) <= ABS_LP
     # the optimiser and the tempered chains have moved to high-posterior territory
     assert np.median(lp) > np.median(ch.log_posterior(ch.random_pos(200)))
+
+
+@pytest.mark.parametrize("name", ["c1_matern", "c1_logexp", "c1_nopca", "c1_multi", "odd_shape", "p20_trafo"])
+def test_sampler_on_every_chain_kind(name):
+    """run_mcmc's default sampler has to work on whatever path the chain takes -- diagonal
+    (exp/diag emulators), dense Cholesky (no-PCA), several emulators, the parameter-function
+    pre-transform -- under graph replay: trajectories against the oracle from the device's Philox draws."""
+    from gpbt_b200.device import DeviceChain
+    from gpbt_b200.sampler import DeviceEnsembleSampler
+    if name not in goldens.available():
+        pytest.skip("golden %s not present" % name)
+    g = goldens.load(name)
+    states, sts = product_states(g)
+    dc = DeviceChain(states, g["lo"], g["hi"], g["y_exp"], g["cov_exp"])
+    logp = lambda X: orc.log_posterior(sts, X, g["lo"], g["hi"], g["y_exp"], g["cov_exp"])
+    nw, steps, seed = 2 * len(g["lo"]) + 3, 8, 42
+    x0 = start(g, nw, 3)
+    s = DeviceEnsembleSampler(nw, x0.shape[1], dc, seed=seed)
+    s.set_state(x0)
+    s.advance(steps)
+    u, partner, perm = eo.philox_streams(seed, 0, steps, nw)
+    chain, lps, acc = eo.stretch_run(logp, x0, logp(x0), u, partner, perm)
+    np.testing.assert_array_equal(s.get_chain(), chain)
+    got = s.get_log_prob()
+    fin = np.isfinite(lps)
+    assert np.array_equal(np.isfinite(got), fin) and np.max(np.abs(got[fin] - lps[fin])) <= 2 * ABS_LP
+    np.testing.assert_array_equal(s.n_accepted, acc)
+    s.close()
+    dc.release()
