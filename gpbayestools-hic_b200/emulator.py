@@ -230,6 +230,46 @@ class Emulator:
         the nsamples x nobs x nobs array -- for posterior-predictive and sensitivity sweeps."""
         return self._dev().predict_diag(X, extra_std=extra_std)
 
+    # ---- small helpers the notebooks call (src/emulator.py:100-124, 243-248, 366-375, 608-633) ------
+    def parametrization_zeta_over_s_vs_T(self, zeta_max, T_zeta0, sigma_plus, sigma_minus, T, mu_B):
+        """zeta/s(T): Gaussian bump of height zeta_max around T_zeta0 - 0.15 mu_B^2, width sigma_minus
+        below T_zeta0 and sigma_plus above (scalar or array T)."""
+        centre = T_zeta0 - 0.15 * mu_B ** 2.
+        width = np.where(np.asarray(T) < T_zeta0, sigma_minus, sigma_plus)
+        out = zeta_max * np.exp(-(T - centre) ** 2. / (2. * width ** 2.))
+        return float(out) if np.ndim(out) == 0 else out
+
+    def parametrization_eta_over_s_vs_mu_B(self, eta_0, eta_2, eta_4, mu_B):
+        out = curve_on_grid(1, [[eta_0, eta_2, eta_4]], np.atleast_1d(mu_B))[0]
+        return float(out[0]) if np.ndim(mu_B) == 0 else out
+
+    def parametrization_y_loss_vs_y_init(self, yloss_2, yloss_4, yloss_6, y_init):
+        out = curve_on_grid(2, [[yloss_2, yloss_4, yloss_6]], np.atleast_1d(y_init))[0]
+        return float(out[0]) if np.ndim(y_init) == 0 else out
+
+    def outputPCAvsParam(self):
+        """design points and the first npc principal-component scores of the training data [npc, nev]"""
+        # (a copy: scaler and pca work in place, copy=False as in the reference)
+        Z = self.pca.fit_transform(self.scaler.fit_transform(self.model_data.copy()))[:, :self.npc]
+        return self.design_points, Z.T
+
+    def _inverse_transform(self, Z):
+        """principal components [..., k <= nobs] -> observables [..., nobs]"""
+        return np.dot(Z, self._trans_matrix[:np.shape(Z)[-1]]) + self.scaler.mean_
+
+    def sample_y(self, X, n_samples=1, random_state=None):
+        """Draws of the model output at X, [n_X, n_samples, nobs]: each emulated PC is sampled from its
+        GP (scikit-learn, on the host, as in the reference), the truncated components are standard
+        normal.  Not available without the PCA (the reference has no such path either); X is in the
+        GPs' own input space (the reference does not apply the parameterTrafoPCA transform here)."""
+        if self.perform_no_PCA_:
+            log.warning("Sampling from raw data is not implemented.")
+            return None
+        X = np.atleast_2d(np.asarray(X, dtype=np.float64))
+        draws = [gp.sample_y(X, n_samples=n_samples, random_state=random_state)[:, :, np.newaxis] for gp in self.gps]
+        rest = np.random.standard_normal((X.shape[0], n_samples, self.pca.n_components_ - self.npc))
+        return self._inverse_transform(np.concatenate(draws + [rest], axis=2))
+
     # ---- validation helpers (callers of predict; src/emulator.py:418-421, 636-726) ----------------
     def getAvgTrainingDataRelError(self):
         """mean over the design of (statistical error / value) per observable"""

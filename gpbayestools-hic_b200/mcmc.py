@@ -143,6 +143,10 @@ class Chain:
         """Same values as the reference's N=1 Python loop (src/mcmc.py:225-258), in one batch."""
         return self.device().log_target(X, -np.inf)
 
+    def _read_in_exp_data_pickle(self, filepath):
+        """values [n_entries, nobs] and diag(err^2) [nobs, nobs] of an experiment pickle (src/mcmc.py:302-324)"""
+        return read_experiment_pickle(filepath)
+
     def random_pos(self, n=1):
         return np.random.uniform(self.min, self.max, (n, self.ndim))
 

@@ -229,3 +229,30 @@ def test_stretch_oracle_samples_a_known_gaussian():
     assert 0.3 < acc.mean() / steps < 0.8
     np.testing.assert_array_equal(lps[-1], logp(chain[-1]))
     assert sorted(eo.fixed_split(7)) == list(range(7)) and list(eo.fixed_split(5)) == [0, 2, 4, 1, 3]
+
+
+def test_emulator_small_helpers_match_reference_formulas(tmp_path):
+    """parametrization_* / _inverse_transform / outputPCAvsParam / sample_y of the drop-in Emulator
+    (src/emulator.py:100-124, 243-248, 366-375, 608-633) -- CPU only, no device call."""
+    from gpbt_b200 import synthetic
+    from gpbt_b200.emulator import Emulator
+    paths = synthetic.write_fixture(str(tmp_path), p=3, n=30, m=8)
+    emu = Emulator(training_set_path=paths["train"], parameter_file=paths["par"], npc=3)
+    # scalar formulas, written out independently
+    assert emu.parametrization_zeta_over_s_vs_T(0.2, 0.18, 0.05, 0.02, 0.15, 0.3) == pytest.approx(
+        0.2 * np.exp(-(0.15 - (0.18 - 0.15 * 0.09)) ** 2 / (2 * 0.02 ** 2)))
+    assert emu.parametrization_zeta_over_s_vs_T(0.2, 0.18, 0.05, 0.02, 0.25, 0.0) == pytest.approx(
+        0.2 * np.exp(-(0.25 - 0.18) ** 2 / (2 * 0.05 ** 2)))
+    assert emu.parametrization_eta_over_s_vs_mu_B(0.1, 0.2, 0.4, 0.1) == pytest.approx(0.15)
+    assert emu.parametrization_eta_over_s_vs_mu_B(0.1, 0.2, 0.4, 0.3) == pytest.approx(0.3)
+    assert emu.parametrization_eta_over_s_vs_mu_B(0.1, 0.2, 0.4, 0.0) == pytest.approx(0.4)   # the reference's else branch
+    assert emu.parametrization_y_loss_vs_y_init(1.0, 2.0, 4.0, 1.0) == pytest.approx(0.5)
+    assert emu.parametrization_y_loss_vs_y_init(1.0, 2.0, 4.0, 3.0) == pytest.approx(1.5)
+    assert emu.parametrization_y_loss_vs_y_init(1.0, 2.0, 4.0, 5.0) == pytest.approx(3.0)
+    emu.trainEmulatorAutoMask()
+    X, Z = emu.outputPCAvsParam()
+    assert X.shape == (emu.nev, 3) and Z.shape == (3, emu.nev)
+    back = emu._inverse_transform(Z.T)
+    assert back.shape == (emu.nev, 8) and np.median(np.abs(back - emu.model_data) / np.abs(emu.model_data)) < 0.05
+    ys = emu.sample_y(emu.design_points[:4], n_samples=5, random_state=0)
+    assert ys.shape == (4, 5, 8) and np.all(np.isfinite(ys))
