@@ -13,6 +13,7 @@
 #include "backtransform.cuh"
 #include "chol_loglike.cuh"
 #include "chol_staged.cuh"
+#include "chol_stepped.cuh"
 #include "chol_warp.cuh"
 #include "common.cuh"
 #include "ensemble.cuh"
@@ -444,6 +445,51 @@ int run_backtransform(gpbt_emulator_t e, const double* zm, const double* zv, int
   return 0;
 }
 
+// work vectors of the stepped Cholesky (t, log-determinant, non-PD flag per walker), one set per device
+struct SteppedCache {
+  double* buf = nullptr;
+  size_t bytes = 0;
+};
+SteppedCache g_stepped[kMaxDevices];
+
+int run_chol_stepped(const CholParams& prm, cudaStream_t st) {
+  const int m = prm.m;
+  const int64_t N = prm.N;
+  const int dev = current_device();
+  if (dev < 0 || dev >= kMaxDevices) return fail(GPBT_EINVAL, "device index %d out of range", dev);
+  const size_t need = (size_t)N * (m + 2) * sizeof(double);
+  SteppedCache& c = g_stepped[dev];
+  if (need > c.bytes) {
+    if (c.buf) cudaFree(c.buf);
+    c.buf = nullptr;
+    c.bytes = 0;
+    CU(cudaMalloc(&c.buf, need));
+    c.bytes = need;
+    g_ws_generation++;
+  }
+  SteppedWork wk;
+  wk.tvec = c.buf;
+  wk.logdet = c.buf + (size_t)N * m;
+  wk.bad = reinterpret_cast<int*>(wk.logdet + N);
+  if (prm.cov_add != nullptr) {
+    chol_step_add_kernel<<<dim3(8, (unsigned)N), 256, 0, st>>>(prm);
+    LAUNCH_CHECK();
+  }
+  if (int r = ensure_dynamic_smem<chol_step_factor_kernel>(chol_step_factor_smem_bytes(m))) return r;
+  if (int r = ensure_dynamic_smem<chol_step_update_kernel>(chol_step_update_smem_bytes())) return r;
+  for (int J = 0; J < m; J += kSpNB) {
+    if (J > 0) {
+      const dim3 grid((unsigned)((m - J + kSpRows - 1) / kSpRows), (unsigned)N);
+      chol_step_update_kernel<<<grid, kSpThreads, chol_step_update_smem_bytes(), st>>>(prm, J);
+      LAUNCH_CHECK();
+    }
+    chol_step_factor_kernel<<<(unsigned)N, kSpThreads, chol_step_factor_smem_bytes(m), st>>>(prm, wk, J,
+                                                                                          J + kSpNB >= m ? 1 : 0);
+    LAUNCH_CHECK();
+  }
+  return 0;
+}
+
 int run_chol(const double* mean, const double* y_exp, double* cov, const double* cov_add, double* lp,
              int* n_notpd, const unsigned char* skip, double notpd_value, double add_const, int64_t N, int m,
              cudaStream_t st) {
@@ -467,6 +513,12 @@ int run_chol(const double* mean, const double* y_exp, double* cov, const double*
     LAUNCH_CHECK();
     return 0;
   }
+  // stepped variant (GPBT_CHOL=batch, experimental): all walkers advance panel by panel, two launches
+  // per 32 columns.  Measured slower than the staged kernel at m = 300 (1.33 vs 1.14 ms per 1024
+  // walkers: its update launches run the tensor pipe at 60-75 %, but the ten factor launches cost
+  // 50-75 us each -- one warp per walker in a 32-pivot chain), so it is opt-in only.
+  const bool aligned_rows = (m % 2 == 0) && ((reinterpret_cast<uintptr_t>(cov) & 15) == 0);
+  if (aligned_rows && which && which[0] == 'b') return run_chol_stepped(prm, st);
   // staged kernel (operand stream through a cp.async ring): needs 16-byte aligned rows and its
   // fixed block assignment covers m <= 352
   const size_t ssmem = chol_staged_smem_bytes(m);

@@ -126,20 +126,24 @@ class DeviceEmulator:
         return (mean, cov) if return_cov else mean
 
 
-def mvn_loglike_batch(dY, cov, notpd_value=-np.inf):
-    """Batched mvn_loglike (src/mcmc.py:23-65) for dY [N, m], cov [N, m, m] (NumPy in/out)."""
+def mvn_loglike_batch(dY, cov, notpd_value=-np.inf, cov_add=None):
+    """Batched mvn_loglike (src/mcmc.py:23-65) for dY [N, m], cov [N, m, m] (NumPy in/out); cov_add
+    [m, m], if given, is added to every covariance on the device (cov + expdata_cov, src/mcmc.py:290)."""
     torch = _torch()
     dY = np.ascontiguousarray(np.array(dY, dtype=np.float64, ndmin=2))
     cov = np.ascontiguousarray(np.asarray(cov, dtype=np.float64)).reshape(dY.shape[0], dY.shape[1], dY.shape[1])
     N, m = dY.shape
     out = np.empty(N)
+    add_d = None if cov_add is None else torch.from_numpy(
+        np.ascontiguousarray(cov_add, dtype=np.float64).reshape(m, m)).cuda()
     rows = max(1, min(N, _COV_CHUNK_BYTES // (8 * m * m)))
     for s in range(0, N, rows):
         e = min(N, s + rows)
         y_d = torch.from_numpy(dY[s:e]).cuda()
         c_d = torch.from_numpy(cov[s:e]).cuda()   # device copy; the kernel factorises it in place
         lp_d = torch.empty(e - s, dtype=torch.float64, device="cuda")
-        _lib.check(_lib.lib.gpbt_mvn_loglike(y_d.data_ptr(), None, c_d.data_ptr(), None, lp_d.data_ptr(),
+        _lib.check(_lib.lib.gpbt_mvn_loglike(y_d.data_ptr(), None, c_d.data_ptr(),
+                                             None if add_d is None else add_d.data_ptr(), lp_d.data_ptr(),
                                              None, float(notpd_value), e - s, m, _stream_ptr(torch)))
         out[s:e] = lp_d.cpu().numpy()
     return out

@@ -524,3 +524,31 @@ def test_random_shapes_vs_oracle(shape):
         omean, ocov = orc.emulator_predict(ost, Xi, True, np.full(len(Xi), 0.03))
         assert rel_err(mean, omean) <= REL and scaled_err(cov, ocov) <= REL, shape
     ch.release()
+
+
+@pytest.mark.parametrize("m", [96, 130, 300])
+def test_cholesky_variants_agree(m, monkeypatch):
+    """gpbt_mvn_loglike through each Cholesky kernel that takes this size (staged default, register-fed
+    CTA kernel, warp-per-walker, and the opt-in stepped variant that advances all walkers panel by
+    panel) against scipy's dpotrf/dpotrs on random SPD matrices, with and without cov_add, plus a
+    non-positive-definite matrix."""
+    from gpbt_b200.device import mvn_loglike_batch
+    rng = np.random.default_rng(m)
+    N = 37
+    B = rng.normal(size=(N, m, m + 5))
+    cov = B @ np.swapaxes(B, 1, 2) / m + 0.5 * np.eye(m)
+    add = np.diag(rng.uniform(0.1, 0.3, m))
+    dY = rng.normal(size=(N, m))
+    want = np.array([orc.mvn_loglike(d, c) for d, c in zip(dY, cov)])
+    want_add = np.array([orc.mvn_loglike(d, c + add) for d, c in zip(dY, cov)])
+    bad = cov.copy()
+    bad[5] -= 3.0 * np.eye(m)
+    for which in ("", "cta", "warp", "batch"):
+        if which:
+            monkeypatch.setenv("GPBT_CHOL", which)
+        got = mvn_loglike_batch(dY, cov)
+        assert np.max(np.abs(got - want)) <= ABS_LP, which
+        got = mvn_loglike_batch(dY, cov, cov_add=add)
+        assert np.max(np.abs(got - want_add)) <= ABS_LP, which
+        got = mvn_loglike_batch(dY, bad)
+        assert np.isneginf(got[5]) and np.max(np.abs(np.delete(got, 5) - np.delete(want, 5))) <= ABS_LP, which
