@@ -98,14 +98,20 @@ constexpr int kBtRows = 32;
 
 inline size_t backtransform_smem_bytes(int q_pad, int m_ld) { return sizeof(double) * (size_t)q_pad * m_ld; }
 
-// number of (row tile, column group) items of one walker and the decoding of an item index
+constexpr int kBtNBI = 2;     // n8 column blocks per work item (a 32 x 16 tile)
+constexpr int kBtGroup = 8;   // walkers that share one load of the Ctrunc tile
+
+// number of (row tile, column group) items of one walker
 __host__ __device__ inline int bt_items_per_walker(int m) {
   const int n_rt = (m + kBtRows - 1) / kBtRows, n_nb = (m + 7) / 8;
   int cnt = 0;
-  for (int rt = 0; rt < n_rt; rt++) cnt += (n_nb - 4 * rt + 3) / 4;
+  for (int rt = 0; rt < n_rt; rt++) cnt += (n_nb - 4 * rt + kBtNBI - 1) / kBtNBI;
   return cnt;
 }
 
+// A work item is one 32 x 16 tile position for a group of kBtGroup consecutive walkers: the warp keeps
+// the Ctrunc tile in registers and walks through the group, so Ctrunc is read from L2 once per eight
+// output tiles and its latency is off the path of all but the first.
 __global__ void __launch_bounds__(kBtThreads, 4) backtransform_cov_kernel(const BacktransformParams prm, int q_pad) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int m = prm.m, m_ld = prm.m_ld;
@@ -119,96 +125,110 @@ __global__ void __launch_bounds__(kBtThreads, 4) backtransform_cov_kernel(const 
   }
   __syncthreads();
 
-  const int n_rt = (m + kBtRows - 1) / kBtRows, n_nb = (m + 7) / 8;
+  const int n_nb = (m + 7) / 8;
   const int per_walker = bt_items_per_walker(m);
-  const int64_t n_items = prm.N * per_walker;
+  const int64_t n_groups = (prm.N + kBtGroup - 1) / kBtGroup;
+  const int64_t n_items = n_groups * per_walker;
   const int64_t ldc = prm.ld_cov, off = prm.col_off;
   const bool vec_ok = (ldc % 2 == 0) && (off % 2 == 0) && ((reinterpret_cast<uintptr_t>(prm.cov) & 15) == 0);
   const bool ct_vec = (m % 2 == 0) && ((reinterpret_cast<uintptr_t>(prm.Ctrunc) & 15) == 0);
   const int64_t warp_stride = (int64_t)gridDim.x * kBtWarps;
 
   for (int64_t item = (int64_t)blockIdx.x * kBtWarps + warp; item < n_items; item += warp_stride) {
-    const int64_t w = item / per_walker;
-    int rem = (int)(item - w * per_walker);
+    const int64_t wg = item / per_walker;
+    int rem = (int)(item - wg * per_walker);
     int rt = 0;
-    for (;; rt++) {  // items of a walker are ordered by row tile, then column group
-      const int cnt = (n_nb - 4 * rt + 3) / 4;
+    for (;; rt++) {  // items of a walker group are ordered by row tile, then column group
+      const int cnt = (n_nb - 4 * rt + kBtNBI - 1) / kBtNBI;
       if (rem < cnt) break;
       rem -= cnt;
     }
-    const int i0 = rt * kBtRows, nb_first = 4 * rt, nb0 = nb_first + 4 * rem;
-    const int nb_hi = min(nb0 + 4, n_nb);
-    double* wbase = prm.cov + (size_t)w * ldc * ldc + (size_t)off * ldc + off;  // block (0,0) of this emulator
-    const double* zv = prm.z_var + w * prm.ldz;
+    const int i0 = rt * kBtRows, nb_first = 4 * rt, nb0 = nb_first + kBtNBI * rem;
+    const int nb_hi = min(nb0 + kBtNBI, n_nb);
 
-    double acc[4][4][2];
-    // accumulators start from the Ctrunc tile; lane owns D[8mb + g][8nb + 2t + {0,1}]
+    // the Ctrunc tile; lane owns D[8mb + g][8nb + 2t + {0,1}]
+    double ct[4][kBtNBI][2];
 #pragma unroll
     for (int mb = 0; mb < 4; mb++) {
       const int i = i0 + 8 * mb + g;
 #pragma unroll
-      for (int nb = 0; nb < 4; nb++) {
+      for (int nb = 0; nb < kBtNBI; nb++) {
         const int j = 8 * (nb0 + nb) + 2 * t;
         const bool in = (i < m) && (nb0 + nb < nb_hi);
         if (in && ct_vec && j + 1 < m) {
           const double2 c2 = ldg2(prm.Ctrunc + (size_t)i * m + j);
-          acc[mb][nb][0] = c2.x;
-          acc[mb][nb][1] = c2.y;
+          ct[mb][nb][0] = c2.x;
+          ct[mb][nb][1] = c2.y;
         } else {
-          acc[mb][nb][0] = (in && j < m) ? __ldg(prm.Ctrunc + (size_t)i * m + j) : 0.0;
-          acc[mb][nb][1] = (in && j + 1 < m) ? __ldg(prm.Ctrunc + (size_t)i * m + j + 1) : 0.0;
+          ct[mb][nb][0] = (in && j < m) ? __ldg(prm.Ctrunc + (size_t)i * m + j) : 0.0;
+          ct[mb][nb][1] = (in && j + 1 < m) ? __ldg(prm.Ctrunc + (size_t)i * m + j + 1) : 0.0;
         }
       }
     }
-    for (int k0 = 0; k0 < q_pad; k0 += 4) {
-      const double vk = (k0 + t < prm.q) ? zv[k0 + t] : 0.0;
-      double a[4], b[4];
+
+    const int64_t w_end = min(prm.N, (wg + 1) * kBtGroup);
+#pragma unroll 1
+    for (int64_t w = wg * kBtGroup; w < w_end; w++) {
+      double* wbase = prm.cov + (size_t)w * ldc * ldc + (size_t)off * ldc + off;  // block (0,0) of this emulator
+      const double* zv = prm.z_var + w * prm.ldz;
+      double acc[4][kBtNBI][2];
+#pragma unroll
+      for (int mb = 0; mb < 4; mb++)
+#pragma unroll
+        for (int nb = 0; nb < kBtNBI; nb++) {
+          acc[mb][nb][0] = ct[mb][nb][0];
+          acc[mb][nb][1] = ct[mb][nb][1];
+        }
+      for (int k0 = 0; k0 < q_pad; k0 += 4) {
+        const double vk = (k0 + t < prm.q) ? zv[k0 + t] : 0.0;
+        double a[4], b[kBtNBI];
+#pragma unroll
+        for (int mb = 0; mb < 4; mb++) {
+          const int i = i0 + 8 * mb + g;
+          a[mb] = (i < m_ld) ? vk * As[(size_t)(k0 + t) * m_ld + i] : 0.0;
+        }
+#pragma unroll
+        for (int nb = 0; nb < kBtNBI; nb++) {
+          const int j = 8 * (nb0 + nb) + g;
+          b[nb] = j < m_ld ? As[(size_t)(k0 + t) * m_ld + j] : 0.0;
+        }
+#pragma unroll
+        for (int nb = 0; nb < kBtNBI; nb++)
+          if (nb0 + nb < nb_hi) {
+#pragma unroll
+            for (int mb = 0; mb < 4; mb++) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
+          }
+      }
 #pragma unroll
       for (int mb = 0; mb < 4; mb++) {
         const int i = i0 + 8 * mb + g;
-        a[mb] = (i < m_ld) ? vk * As[(size_t)(k0 + t) * m_ld + i] : 0.0;
-      }
+        if (i >= m) continue;
 #pragma unroll
-      for (int nb = 0; nb < 4; nb++) {
-        const int j = 8 * (nb0 + nb) + g;
-        b[nb] = j < m_ld ? As[(size_t)(k0 + t) * m_ld + j] : 0.0;
-      }
-#pragma unroll
-      for (int nb = 0; nb < 4; nb++)
-        if (nb0 + nb < nb_hi) {
-#pragma unroll
-          for (int mb = 0; mb < 4; mb++) dmma884(acc[mb][nb][0], acc[mb][nb][1], a[mb], b[nb]);
-        }
-    }
-#pragma unroll
-    for (int mb = 0; mb < 4; mb++) {
-      const int i = i0 + 8 * mb + g;
-      if (i >= m) continue;
-#pragma unroll
-      for (int nb = 0; nb < 4; nb++) {
-        const int j = 8 * (nb0 + nb) + 2 * t;
-        if (nb0 + nb >= nb_hi || j >= m) continue;
-        double* row = wbase + (size_t)i * ldc;
-        if (vec_ok && j + 1 < m) {
-          *reinterpret_cast<double2*>(row + j) = make_double2(acc[mb][nb][0], acc[mb][nb][1]);
-        } else {
-          row[j] = acc[mb][nb][0];
-          if (j + 1 < m) row[j + 1] = acc[mb][nb][1];
-        }
-        // mirror of the blocks right of the diagonal 32x32 tile: cov[j][i] = cov[i][j]
-        if (nb0 + nb >= nb_first + 4) {
-          wbase[(size_t)j * ldc + i] = acc[mb][nb][0];
-          if (j + 1 < m) wbase[(size_t)(j + 1) * ldc + i] = acc[mb][nb][1];
+        for (int nb = 0; nb < kBtNBI; nb++) {
+          const int j = 8 * (nb0 + nb) + 2 * t;
+          if (nb0 + nb >= nb_hi || j >= m) continue;
+          double* row = wbase + (size_t)i * ldc;
+          if (vec_ok && j + 1 < m) {
+            *reinterpret_cast<double2*>(row + j) = make_double2(acc[mb][nb][0], acc[mb][nb][1]);
+          } else {
+            row[j] = acc[mb][nb][0];
+            if (j + 1 < m) row[j + 1] = acc[mb][nb][1];
+          }
+          // mirror of the blocks right of the diagonal 32x32 tile: cov[j][i] = cov[i][j]
+          if (nb0 + nb >= nb_first + 4) {
+            wbase[(size_t)j * ldc + i] = acc[mb][nb][0];
+            if (j + 1 < m) wbase[(size_t)(j + 1) * ldc + i] = acc[mb][nb][1];
+          }
         }
       }
-    }
-    // zero the parts of these rows that lie outside the diagonal block (multi-emulator chains);
-    // done by the item that owns the diagonal tile of the row tile
-    if (ldc > m && rem == 0) {
-      double* rows0 = prm.cov + ((size_t)w * ldc + off + i0) * ldc;
-      for (int r = 0; r < kBtRows && i0 + r < m; r++)
-        for (int64_t cidx = lane; cidx < ldc; cidx += 32)
-          if (cidx < off || cidx >= off + m) rows0[(size_t)r * ldc + cidx] = 0.0;
+      // zero the parts of these rows that lie outside the diagonal block (multi-emulator chains);
+      // done by the item that owns the diagonal tile of the row tile
+      if (ldc > m && rem == 0) {
+        double* rows0 = prm.cov + ((size_t)w * ldc + off + i0) * ldc;
+        for (int r = 0; r < kBtRows && i0 + r < m; r++)
+          for (int64_t cidx = lane; cidx < ldc; cidx += 32)
+            if (cidx < off || cidx >= off + m) rows0[(size_t)r * ldc + cidx] = 0.0;
+      }
     }
   }
 }

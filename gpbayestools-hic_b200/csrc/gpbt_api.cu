@@ -435,7 +435,7 @@ int run_backtransform(gpbt_emulator_t e, const double* zm, const double* zv, int
     if (smem > (size_t)max_optin_smem())
       return fail(GPBT_ESHAPE, "backtransform: q*m = %d*%d does not fit in shared memory", e->q, e->m);
     if (int r = ensure_dynamic_smem<backtransform_cov_kernel>(smem)) return r;
-    const int64_t items = N * bt_items_per_walker(e->m);      // one per warp
+    const int64_t items = ((N + kBtGroup - 1) / kBtGroup) * bt_items_per_walker(e->m);   // one per warp
     int per_sm = (int)std::min<size_t>(4, (228 * 1024 - 4096) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
     const unsigned grid = (unsigned)std::min<int64_t>((items + kBtWarps - 1) / kBtWarps, (int64_t)148 * per_sm);
