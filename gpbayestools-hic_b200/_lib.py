@@ -21,7 +21,8 @@ SYMBOLS = [
     "gpbt_log_posterior_host",
     "gpbt_chain_workspace_bytes", "gpbt_launch_count", "gpbt_debug_exp_neg",
     "gpbt_host_temp_exchange", "gpbt_ensemble_create", "gpbt_ensemble_destroy", "gpbt_ensemble_set_state", "gpbt_ensemble_get_state",
-    "gpbt_ensemble_run", "gpbt_ensemble_steps", "gpbt_ensemble_reserve", "gpbt_ensemble_read", "gpbt_ensemble_reset",
+    "gpbt_ensemble_run", "gpbt_ensemble_steps", "gpbt_ensemble_reserve",
+    "gpbt_ensemble_prepare", "gpbt_ensemble_begin_half", "gpbt_ensemble_copy_proposals", "gpbt_ensemble_end_half", "gpbt_ensemble_read", "gpbt_ensemble_reset",
 ]
 
 
@@ -66,6 +67,10 @@ def _load():
     lib.gpbt_ensemble_steps.argtypes = [vp]
     lib.gpbt_ensemble_steps.restype = i64
     lib.gpbt_ensemble_reserve.argtypes = [vp, i64]
+    lib.gpbt_ensemble_prepare.argtypes = [vp, i64]
+    lib.gpbt_ensemble_begin_half.argtypes = [vp, i32, vp]
+    lib.gpbt_ensemble_copy_proposals.argtypes = [vp, i32, i64, i64, dp, vp]
+    lib.gpbt_ensemble_end_half.argtypes = [vp, i32, dp, vp]
     lib.gpbt_ensemble_read.argtypes = [vp, i64, i64, dp, dp, dp, dp]
     lib.gpbt_ensemble_reset.argtypes = [vp]
     return lib

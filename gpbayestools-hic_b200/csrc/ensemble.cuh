@@ -243,6 +243,18 @@ __global__ void __launch_bounds__(256) ensemble_record_kernel(EnsembleCtl* __res
   }
 }
 
+// rows [first, first + n) of the proposal buffer into dst (row index clamped to the active set: callers
+// that shard the proposals over ranks pad their last block by repeating the last row)
+__global__ void ensemble_gather_rows_kernel(const double* __restrict__ q, int64_t ns, int p, int64_t first, int64_t n,
+                                            double* __restrict__ dst) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * p) return;
+  const int64_t r = idx / p;
+  const int d = (int)(idx - r * p);
+  const int64_t src = min(first + r, ns - 1);
+  dst[idx] = q[src * p + d];
+}
+
 // ---- launch shape 2: small ensembles (a step is launch-latency bound), one CTA, three kernels -------
 //   begin = split + propose(0);   mid = accept(0) + propose(1);   end = accept(1) + record
 constexpr int kEnsembleFusedMaxWalkers = 2048;

@@ -1090,6 +1090,7 @@ struct gpbt_ensemble {
   long long *accepted = nullptr, *notpd_total = nullptr;
   double *hist_x = nullptr, *hist_lp = nullptr;
   int64_t hist_cap = 0, steps = 0;
+  int64_t prepared_until = 0;            // steps the history / control block have room for (piecewise stepping)
   double* ru = nullptr;                  // device copies of the host random streams of the current run
   int *rp = nullptr, *perm_in = nullptr;
   cudaGraphExec_t graph = nullptr;
@@ -1253,13 +1254,14 @@ extern "C" int gpbt_ensemble_get_state(gpbt_ensemble_t en, double* X_host, doubl
   return 0;
 }
 
-extern "C" int gpbt_ensemble_run(gpbt_ensemble_t en, int64_t n_steps, const double* u_host,
-                                 const int32_t* partner_host, const int32_t* perm_host, int use_graph) {
-  if (!en || n_steps < 0) return fail(GPBT_EINVAL, "gpbt_ensemble_run: bad argument");
-  if (!en->has_state) return fail(GPBT_EINVAL, "gpbt_ensemble_run: call gpbt_ensemble_set_state first");
+namespace {
+// room for n_steps more steps, the optional host draws on the device, and the control block
+int ensemble_prepare(gpbt_ensemble* en, int64_t n_steps, const double* u_host, const int32_t* partner_host,
+                     const int32_t* perm_host) {
+  if (!en || n_steps < 0) return fail(GPBT_EINVAL, "gpbt_ensemble: bad argument");
+  if (!en->has_state) return fail(GPBT_EINVAL, "gpbt_ensemble: call gpbt_ensemble_set_state first");
   if ((u_host == nullptr) != (partner_host == nullptr))
-    return fail(GPBT_EINVAL, "gpbt_ensemble_run: u_host and partner_host come together");
-  if (n_steps == 0) return 0;
+    return fail(GPBT_EINVAL, "gpbt_ensemble: u_host and partner_host come together");
   CU(cudaSetDevice(en->ch->device));
   cudaStream_t st = en->ch->stream;
   if (int r = ensemble_grow_history(en, en->steps + n_steps, st)) return r;
@@ -1273,6 +1275,76 @@ extern "C" int gpbt_ensemble_run(gpbt_ensemble_t en, int64_t n_steps, const doub
   h.hist_x = en->hist_x; h.hist_lp = en->hist_lp;
   CU(cudaMemcpyAsync(en->ctl, &h, sizeof h, cudaMemcpyHostToDevice, st));
   CU(cudaStreamSynchronize(st));   // h lives on this stack frame
+  en->prepared_until = en->steps + n_steps;
+  return 0;
+}
+}  // namespace
+
+// ---- a sampler step in pieces, for callers that evaluate the proposals themselves -----------------
+extern "C" int gpbt_ensemble_prepare(gpbt_ensemble_t en, int64_t n_steps) {
+  return ensemble_prepare(en, n_steps, nullptr, nullptr, nullptr);
+}
+
+extern "C" int gpbt_ensemble_begin_half(gpbt_ensemble_t en, int half, void* stream) {
+  if (!en || (half != 0 && half != 1)) return fail(GPBT_EINVAL, "gpbt_ensemble_begin_half: bad argument");
+  if (en->steps >= en->prepared_until)
+    return fail(GPBT_EINVAL, "gpbt_ensemble_begin_half: no prepared step left (call gpbt_ensemble_prepare)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nw = en->nw;
+  const EnsembleBuffers b = ensemble_buffers(en);
+  if (half == 0) {
+    ensemble_keys_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(en->ctl, en->seed, nw, en->randomize, en->keys,
+                                                                      en->perm);
+    LAUNCH_CHECK();
+    ensemble_rank_kernel<<<(unsigned)((nw + kRankThreads - 1) / kRankThreads), kRankThreads, 0, st>>>(
+        en->ctl, nw, en->randomize, en->keys, en->perm);
+    LAUNCH_CHECK();
+  }
+  const int ns = half == 0 ? en->n_half : nw - en->n_half;
+  if (ns > 0) {
+    ensemble_propose_kernel<<<(unsigned)((ns + 127) / 128), 128, 0, st>>>(b, half);
+    LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int gpbt_ensemble_copy_proposals(gpbt_ensemble_t en, int half, int64_t first, int64_t n, double* dst_dev,
+                                            void* stream) {
+  if (!en || !dst_dev || first < 0 || n < 0) return fail(GPBT_EINVAL, "gpbt_ensemble_copy_proposals: bad argument");
+  const int64_t ns = half == 0 ? en->n_half : en->nw - en->n_half;
+  if (n == 0) return 0;
+  if (ns == 0) return fail(GPBT_EINVAL, "gpbt_ensemble_copy_proposals: the active set is empty");
+  ensemble_gather_rows_kernel<<<(unsigned)((n * en->p + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      en->q, ns, en->p, first, n, dst_dev);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int gpbt_ensemble_end_half(gpbt_ensemble_t en, int half, const double* lp_new_dev, void* stream) {
+  if (!en || !lp_new_dev || (half != 0 && half != 1)) return fail(GPBT_EINVAL, "gpbt_ensemble_end_half: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nw = en->nw, p = en->p;
+  EnsembleBuffers b = ensemble_buffers(en);
+  b.lp_new = lp_new_dev;
+  const int ns = half == 0 ? en->n_half : nw - en->n_half;
+  if (ns > 0) {
+    ensemble_accept_kernel<<<(unsigned)((ns + 127) / 128), 128, 0, st>>>(b, half);
+    LAUNCH_CHECK();
+  }
+  if (half == 1) {
+    const unsigned rec_grid = (unsigned)std::min<int64_t>(((int64_t)nw * p + 255) / 256, 148);
+    ensemble_record_kernel<<<rec_grid, 256, 0, st>>>(en->ctl, nw, p, en->x, en->lp, en->rec_done);
+    LAUNCH_CHECK();
+    en->steps += 1;
+  }
+  return 0;
+}
+
+extern "C" int gpbt_ensemble_run(gpbt_ensemble_t en, int64_t n_steps, const double* u_host,
+                                 const int32_t* partner_host, const int32_t* perm_host, int use_graph) {
+  if (int r = ensemble_prepare(en, n_steps, u_host, partner_host, perm_host)) return r;
+  if (n_steps == 0) return 0;
+  cudaStream_t st = en->ch->stream;
 
   int64_t done = 0;
   // graph replay pays off where a step is launch bound; large ensembles (separate-kernel shape) are
@@ -1355,6 +1427,7 @@ extern "C" int gpbt_ensemble_reset(gpbt_ensemble_t en) {
   CU(cudaMemsetAsync(en->accepted, 0, (size_t)en->nw * sizeof(long long), en->ch->stream));
   CU(cudaStreamSynchronize(en->ch->stream));
   en->steps = 0;
+  en->prepared_until = 0;   // the device step counter is rewritten by the next prepare / run
   return 0;
 }
 

@@ -214,6 +214,22 @@ int gpbt_ensemble_get_state(gpbt_ensemble_t ens, double* X_host, double* lp_host
 int gpbt_ensemble_run(gpbt_ensemble_t ens, int64_t n_steps, const double* u_host,
                       const int32_t* partner_host, const int32_t* perm_host, int use_graph);
 
+/* The same step in pieces, for callers that evaluate the proposals themselves -- e.g. one process
+ * per GPU with replicated walkers (same seed on every rank -> identical proposals), each rank
+ * evaluating a slice and the log-posteriors all-gathered (gpbt_log_posterior_scatter):
+ *   gpbt_ensemble_prepare(n_steps)            room in the history for n_steps more steps
+ *   gpbt_ensemble_begin_half(half)            (half 0: new split of the walkers) + stretch proposals
+ *   gpbt_ensemble_copy_proposals(half, first, n, dst_dev)   proposal rows [first, first+n) -> dst_dev[n,p]
+ *                                             (rows past the active set repeat its last row)
+ *   gpbt_ensemble_end_half(half, lp_new_dev)  accept with lp_new_dev[i] = log-posterior of proposal i;
+ *                                             half 1 also appends the step to the history
+ * These only enqueue on `stream`; the caller orders them against its own work there.          */
+int gpbt_ensemble_prepare(gpbt_ensemble_t ens, int64_t n_steps);
+int gpbt_ensemble_begin_half(gpbt_ensemble_t ens, int half, void* stream);
+int gpbt_ensemble_copy_proposals(gpbt_ensemble_t ens, int half, int64_t first, int64_t n, double* dst_dev,
+                                 void* stream);
+int gpbt_ensemble_end_half(gpbt_ensemble_t ens, int half, const double* lp_new_dev, void* stream);
+
 /* steps in the history since the last reset                                                  */
 int64_t gpbt_ensemble_steps(gpbt_ensemble_t ens);
 /* make room for n_steps more steps of history in one allocation (optional; run grows it)     */
