@@ -66,6 +66,33 @@ __device__ __forceinline__ unsigned long long split_key(uint64_t seed, long long
   return ((((unsigned long long)r[0] << 32) | r[1]) & ~0xFFFFFFull) | (unsigned long long)j;
 }
 
+// Large ensembles: ranking n keys against each other is O(n^2) (5 ms per step at 262144 walkers), so
+// above kEnsembleRankMaxWalkers the split permutation is a keyed bijection of [0, n) instead: a 4-round
+// Feistel network on the next power of four, round function = Philox, cycle-walked back into range
+// (at most 4 iterations expected).  perm[i] = feistel(i): O(n), no communication between threads.
+constexpr int kEnsembleRankMaxWalkers = 2048;
+constexpr uint32_t kTagFeistel = 8;   // tags 8..11: the four round functions
+
+__device__ __forceinline__ int split_feistel(uint64_t seed, long long step, int i, int nw) {
+  int hbits = 1;
+  while ((1ll << (2 * hbits)) < (long long)nw) hbits++;
+  const uint32_t mask = (1u << hbits) - 1u;
+  uint32_t x = (uint32_t)i;
+  do {
+    uint32_t l = x >> hbits, r = x & mask;
+#pragma unroll 1
+    for (uint32_t rd = 0; rd < 4; rd++) {
+      uint32_t f[4];
+      philox4x32(seed, (uint64_t)step, r, kTagFeistel + rd, f);
+      const uint32_t nl = r;
+      r = l ^ (f[0] & mask);
+      l = nl;
+    }
+    x = (l << hbits) | r;
+  } while (x >= (uint32_t)nw);
+  return (int)x;
+}
+
 // ---- the three pieces of a step, as device functions shared by the two launch shapes ---------------
 //
 // Random split of the walkers into two sets: perm[0:n0] is set 0, perm[n0:] set 1.  perm is the
@@ -185,6 +212,8 @@ __global__ void ensemble_keys_kernel(const EnsembleCtl* __restrict__ ctl, uint64
     perm[j] = ctl->perm_in[(step - ctl->run_first) * nw + j];
   } else if (!randomize) {
     perm[(j & 1) ? (nw + 1) / 2 + (j >> 1) : (j >> 1)] = j;
+  } else if (nw > kEnsembleRankMaxWalkers) {
+    perm[j] = split_feistel(seed, step, j, nw);
   } else {
     keys[j] = split_key(seed, step, j);
   }
@@ -195,7 +224,7 @@ __global__ void __launch_bounds__(kRankThreads) ensemble_rank_kernel(const Ensem
                                                                       const unsigned long long* __restrict__ keys,
                                                                       int* __restrict__ perm) {
   __shared__ unsigned long long tile[kRankTile];
-  if (ctl->perm_in || !randomize) return;   // perm was written by ensemble_keys_kernel
+  if (ctl->perm_in || !randomize || nw > kEnsembleRankMaxWalkers) return;   // perm was written by ensemble_keys_kernel
   const int j = blockIdx.x * kRankThreads + threadIdx.x;
   const unsigned long long kj = j < nw ? keys[j] : 0ull;
   int rank = 0;

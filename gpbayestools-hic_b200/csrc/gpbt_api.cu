@@ -1136,9 +1136,11 @@ int ensemble_enqueue_step(gpbt_ensemble* en, cudaStream_t st) {
   ensemble_keys_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(en->ctl, en->seed, nw, en->randomize, en->keys,
                                                                     en->perm);
   LAUNCH_CHECK();
-  ensemble_rank_kernel<<<(unsigned)((nw + kRankThreads - 1) / kRankThreads), kRankThreads, 0, st>>>(
-      en->ctl, nw, en->randomize, en->keys, en->perm);
-  LAUNCH_CHECK();
+  if (nw <= kEnsembleRankMaxWalkers) {
+    ensemble_rank_kernel<<<(unsigned)((nw + kRankThreads - 1) / kRankThreads), kRankThreads, 0, st>>>(
+        en->ctl, nw, en->randomize, en->keys, en->perm);
+    LAUNCH_CHECK();
+  }
   for (int half = 0; half < 2; half++) {
     const int ns = half == 0 ? en->n_half : nw - en->n_half;
     if (ns == 0) continue;
@@ -1296,9 +1298,11 @@ extern "C" int gpbt_ensemble_begin_half(gpbt_ensemble_t en, int half, void* stre
     ensemble_keys_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(en->ctl, en->seed, nw, en->randomize, en->keys,
                                                                       en->perm);
     LAUNCH_CHECK();
-    ensemble_rank_kernel<<<(unsigned)((nw + kRankThreads - 1) / kRankThreads), kRankThreads, 0, st>>>(
-        en->ctl, nw, en->randomize, en->keys, en->perm);
-    LAUNCH_CHECK();
+    if (nw <= kEnsembleRankMaxWalkers) {
+      ensemble_rank_kernel<<<(unsigned)((nw + kRankThreads - 1) / kRankThreads), kRankThreads, 0, st>>>(
+          en->ctl, nw, en->randomize, en->keys, en->perm);
+      LAUNCH_CHECK();
+    }
   }
   const int ns = half == 0 ? en->n_half : nw - en->n_half;
   if (ns > 0) {

@@ -49,6 +49,30 @@ def _u01(hi, lo):
     return float(((hi << 32) | lo) >> 11) * (1.0 / 9007199254740992.0)
 
 
+RANK_MAX_WALKERS = 2048   # above this the device splits with a keyed bijection instead of ranking keys
+
+
+def feistel_perm(seed, step, nw):
+    """perm[i] = 4-round Feistel network on the next power of four >= nw (round function: Philox word 0,
+    tags 8..11), cycle-walked into [0, nw) -- csrc/ensemble.cuh split_feistel."""
+    hbits = 1
+    while (1 << (2 * hbits)) < nw:
+        hbits += 1
+    mask = (1 << hbits) - 1
+    out = np.empty(nw, dtype=np.int32)
+    for i in range(nw):
+        x = i
+        while True:
+            l, r = x >> hbits, x & mask
+            for rd in range(4):
+                l, r = r, l ^ (philox4x32(seed, step, r, 8 + rd)[0] & mask)
+            x = (l << hbits) | r
+            if x < nw:
+                break
+        out[i] = x
+    return out
+
+
 def philox_streams(seed, first_step, nsteps, nw):
     """The draws the device generates for steps [first_step, first_step + nsteps): tag 0/1 = uniforms
     of the two half steps, 3/4 = partner draws, 2 = split keys (csrc/ensemble.cuh)."""
@@ -58,11 +82,14 @@ def philox_streams(seed, first_step, nsteps, nw):
     perm = np.zeros((nsteps, nw), dtype=np.int32)
     for s in range(nsteps):
         step = first_step + s
-        keys = []
-        for j in range(nw):
-            r = philox4x32(seed, step, j, 2)
-            keys.append(((((r[0] << 32) | r[1]) & ~0xFFFFFF) | j, j))   # 40 random bits above the index
-        perm[s] = [j for _, j in sorted(keys)]
+        if nw > RANK_MAX_WALKERS:
+            perm[s] = feistel_perm(seed, step, nw)
+        else:
+            keys = []
+            for j in range(nw):
+                r = philox4x32(seed, step, j, 2)
+                keys.append(((((r[0] << 32) | r[1]) & ~0xFFFFFF) | j, j))   # 40 random bits above the index
+            perm[s] = [j for _, j in sorted(keys)]
         for half in range(2):
             ns = n0 if half == 0 else nw - n0
             nc = nw - ns
