@@ -38,6 +38,17 @@ def mvn_loglike(y, cov):
     return float(val)
 
 
+def _dist_world():
+    """(world size, rank) of the default torch.distributed group, (1, 0) when there is none"""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_world_size(), dist.get_rank()
+    except ImportError:
+        pass
+    return 1, 0
+
+
 def read_experiment_pickle(path):
     """Experimental data in the training-pickle layout (src/mcmc.py:302-324): returns the values
     [n_entries, m] and the diagonal covariance diag(err^2) [m, m] of the flattened errors."""
@@ -183,9 +194,18 @@ class Chain:
         if self.mcmc_path.exists():
             with open(self.mcmc_path, "rb") as fh:
                 stored = pickle.load(fh)
-        if sampler == "device":
+        world, rank = _dist_world()
+        if sampler == "device" and world > 1:
+            # one process per GPU (torchrun): replicated walkers, proposals evaluated in slices.  Every
+            # rank must arrive here with the same NumPy seed (starting positions) and the same `seed`.
+            from .sampler import ShardedEnsembleSampler
+            if seed is None:
+                seed = int(np.random.randint(0, 2 ** 31 - 1))
+            ens = ShardedEnsembleSampler(nwalkers, self.ndim, self.device(), seed=seed)
+        elif sampler == "device":
             from .sampler import DeviceEnsembleSampler
             ens = DeviceEnsembleSampler(nwalkers, self.ndim, self.device(), seed=seed)
+        if sampler == "device":
 
             def advance(x0, steps):
                 return ens.run_mcmc(x0, steps, status=status, skip_initial_state_check=skip_initial_state_check)
@@ -221,8 +241,9 @@ class Chain:
         self.acceptance_fraction_ = np.asarray(ens.acceptance_fraction)
         self.chain = np.concatenate((stored["chain"], thinned), axis=1) if "chain" in stored else thinned
         stored["chain"] = self.chain
-        with open(self.mcmc_path, "wb") as fh:
-            pickle.dump(stored, fh)
+        if rank == 0:   # under torchrun every rank holds the same chain; one of them writes it
+            with open(self.mcmc_path, "wb") as fh:
+                pickle.dump(stored, fh)
         if sampler == "device":
             ens.close()
 

@@ -31,4 +31,5 @@ def test_sharded_ensemble_sampler_two_ranks():
            "--master-addr", "127.0.0.1", "--master-port", "29578",
            os.path.join(ROOT, "tools", "sharded_sampler_probe.py"), "1001", "10"]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
-    assert res.returncode == 0 and "SHARDED_SAMPLER_PASS" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+    assert res.returncode == 0 and "SHARDED_SAMPLER_PASS" in res.stdout and "RUN_MCMC_SHARDED_PASS" in res.stdout, \
+        res.stdout[-2000:] + res.stderr[-2000:]

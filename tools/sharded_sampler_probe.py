@@ -71,5 +71,32 @@ if rank == 0:
            "acceptance": float(sh.acceptance_fraction.mean())})
     print("SHARDED_SAMPLER_PASS" if ok else "SHARDED_SAMPLER_FAIL")
 sh.close(); single.close(); chain.release()
+
+# Chain.run_mcmc under torchrun picks the sharded sampler by itself; the chain file is written by rank 0
+import pickle  # noqa: E402
+import tempfile  # noqa: E402
+
+from gpbt_b200 import synthetic  # noqa: E402
+from gpbt_b200.mcmc import Chain  # noqa: E402
+from tests.helpers import product_states  # noqa: E402
+
+g1 = goldens.load("c1_rbf")
+tmp = tempfile.mkdtemp(prefix="gpbt_rank%d_" % rank)
+paths = synthetic.write_fixture(tmp, p=5, n=8, m=50)
+os.makedirs(os.path.join(tmp, "mcmc"), exist_ok=True)
+ch = Chain(mcmc_path=os.path.join(tmp, "mcmc", "chain.pkl"), expdata_path=paths["exp"], model_parafile=paths["par"])
+ch.emuList = product_states(g1)[0]
+np.random.seed(3)
+ch.run_mcmc(nsteps=12, nburnsteps=8, nwalkers=20, nthin=2, seed=9)
+chk = torch.tensor([float(np.sum(ch.chain))], dtype=torch.float64, device="cuda")
+lo_, hi_ = chk.clone(), chk.clone()
+dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
+dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+ok2 = bool(torch.equal(lo_, hi_)) and ch.chain.shape == (20, 6, 5) and (os.path.exists(ch.mcmc_path) == (rank == 0))
+if rank == 0:
+    with open(ch.mcmc_path, "rb") as fh:
+        ok2 = ok2 and pickle.load(fh)["chain"].shape == (20, 6, 5)
+    print("RUN_MCMC_SHARDED_PASS" if ok2 else "RUN_MCMC_SHARDED_FAIL")
+ok = ok and ok2
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
