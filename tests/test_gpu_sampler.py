@@ -255,3 +255,23 @@ def test_sampler_on_every_chain_kind(name):
     np.testing.assert_array_equal(s.n_accepted, acc)
     s.close()
     dc.release()
+
+
+@pytest.mark.parametrize("nw", [2, 3, 5, 2048, 2049])
+def test_ensemble_size_boundaries(c1, nw):
+    """Smallest ensembles (one walker per set), and both sides of the switch from key ranking to the
+    keyed-bijection split (2048 / 2049 walkers) -- device Philox draws against the oracle's."""
+    from gpbt_b200.sampler import DeviceEnsembleSampler
+    g, dc, logp = c1
+    steps, seed = 3, 2026
+    x0 = start(g, nw, 21)
+    s = DeviceEnsembleSampler(nw, x0.shape[1], dc, seed=seed)
+    s.set_state(x0)
+    s.advance(steps)
+    u, partner, perm = eo.philox_streams(seed, 0, steps, nw)
+    for k in range(steps):
+        assert sorted(perm[k]) == list(range(nw))
+    chain, lps, acc = eo.stretch_run(logp, x0, logp(x0), u, partner, perm)
+    np.testing.assert_array_equal(s.get_chain(), chain)
+    np.testing.assert_array_equal(s.n_accepted, acc)
+    s.close()
