@@ -1061,7 +1061,10 @@ extern "C" int gpbt_log_posterior_host(gpbt_chain_t ch, const double* X_host, do
     memcpy(ch->zc_x_host, X_host, (size_t)N * ch->p * sizeof(double));
     int* cnt_host = reinterpret_cast<int*>(ch->zc_lp_host + kZeroCopyRows);
     int* cnt_dev = reinterpret_cast<int*>(ch->zc_lp_dev + kZeroCopyRows);
-    if (int r = gpbt_log_posterior(ch, ch->zc_x_dev, oob_value, ch->zc_lp_dev, cnt_dev, N, path, st)) return r;
+    *cnt_host = 0;   // mapped memory: the host clears the counter itself, no memset node on the stream
+    if (int r = log_posterior_impl(ch, ch->zc_x_dev, oob_value, ch->zc_lp_dev, cnt_dev, N, path, st, nullptr, 0, 0,
+                                   /*zero_counter=*/false))
+      return r;
     CU(cudaStreamSynchronize(st));
     memcpy(lp_host, ch->zc_lp_host, (size_t)N * sizeof(double));
     if (n_notpd_host) *n_notpd_host = *cnt_host;
