@@ -256,3 +256,35 @@ def test_emulator_small_helpers_match_reference_formulas(tmp_path):
     assert back.shape == (emu.nev, 8) and np.median(np.abs(back - emu.model_data) / np.abs(emu.model_data)) < 0.05
     ys = emu.sample_y(emu.design_points[:4], n_samples=5, random_state=0)
     assert ys.shape == (4, 5, 8) and np.all(np.isfinite(ys))
+
+
+def test_emulator_band_host_side(tmp_path):
+    """EmulatorBAND without a GPU: constructor on the reference's file formats, the surmise-free
+    training error, state extraction from surmise-shaped fit information (hypind sharing, amplitudes)."""
+    from gpbt_b200 import synthetic
+    from gpbt_b200.emulator_band import EmulatorBAND
+    from gpbt_b200.state import EmulatorState
+    paths = synthetic.write_fixture(str(tmp_path), p=3, n=25, m=7)
+    emu = EmulatorBAND(training_set_path=paths["train"], parameter_file=paths["par"], method="PCSK")
+    assert emu.nobs == 7 and emu.nparameters == 3 and emu.design_min.shape == (3,)
+    with pytest.raises(ValueError):
+        EmulatorBAND(training_set_path=paths["train"], parameter_file=paths["par"], method="nope")
+    with pytest.raises(ValueError):
+        EmulatorBAND(training_set_path=paths["train"], parameter_file=paths["par"], exp_and_cov_diagonal=True)
+    with pytest.raises(ImportError, match="surmise"):
+        emu.trainEmulatorAutoMask()
+    with pytest.raises(RuntimeError):
+        emu.state
+    info = synthetic.pcgp_fitinfo(3, 25, 7, 4)
+    st = EmulatorState.from_pcgp_fitinfo(info, extravar_in_cov=True)
+    assert st.kind == "PCGP" and (st.p, st.n, st.q, st.m) == (3, 25, 4, 7)
+    g = np.exp(st.pcgp["hypcov"][:, -1])
+    np.testing.assert_allclose(st.c + st.sn, 1.0 - st.pcgp["nug"])                 # (1-nug)(a + b), a + b = 1
+    np.testing.assert_allclose(st.sn / st.c, g)
+    np.testing.assert_array_equal(st.Linv, np.swapaxes(st.pcgp["Vh"], 1, 2))
+    np.testing.assert_allclose(np.diag(st.Ctrunc), info["extravar"])
+    np.testing.assert_array_equal(st.pcgp["hypcov"][1], st.pcgp["hypcov"][0])     # PC 1 shares PC 0's hyper-parameters
+    # the fabricated fit interpolates its own training scores: r(theta_i) . pw = g_i up to the nugget
+    from oracle import gp_oracle as orc
+    zm, zv = orc.pc_predict(st.oracle_dict(), info["theta"])
+    assert zv.max() < 0.05 * st.sig2.max() and np.all(zv >= 0)
