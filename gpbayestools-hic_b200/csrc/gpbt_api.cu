@@ -457,7 +457,7 @@ int run_chol_stepped(const CholParams& prm, cudaStream_t st) {
   const int64_t N = prm.N;
   const int dev = current_device();
   if (dev < 0 || dev >= kMaxDevices) return fail(GPBT_EINVAL, "device index %d out of range", dev);
-  const size_t need = (size_t)N * (m + 2) * sizeof(double);
+  const size_t need = (size_t)N * ((size_t)m + kSpNB * kSpNB + 3) * sizeof(double);
   SteppedCache& c = g_stepped[dev];
   if (need > c.bytes) {
     if (c.buf) cudaFree(c.buf);
@@ -468,24 +468,26 @@ int run_chol_stepped(const CholParams& prm, cudaStream_t st) {
     g_ws_generation++;
   }
   SteppedWork wk;
-  wk.tvec = c.buf;
-  wk.logdet = c.buf + (size_t)N * m;
-  wk.bad = reinterpret_cast<int*>(wk.logdet + N);
+  wk.dinv = c.buf;                                  // first: 16-byte aligned rows for cp.async
+  wk.tvec = wk.dinv + (size_t)N * kSpNB * kSpNB;
+  wk.logdet = wk.tvec + (size_t)N * m;
+  wk.tsq = wk.logdet + N;
+  wk.bad = reinterpret_cast<int*>(wk.tsq + N);
   if (prm.cov_add != nullptr) {
     chol_step_add_kernel<<<dim3(8, (unsigned)N), 256, 0, st>>>(prm);
     LAUNCH_CHECK();
   }
-  if (int r = ensure_dynamic_smem<chol_step_factor_kernel>(chol_step_factor_smem_bytes(m))) return r;
-  if (int r = ensure_dynamic_smem<chol_step_update_kernel>(chol_step_update_smem_bytes())) return r;
+  if (int r = ensure_dynamic_smem<chol_step_diag_kernel>(chol_step_diag_smem_bytes(m))) return r;
+  if (int r = ensure_dynamic_smem<chol_step_below_kernel>(chol_step_below_smem_bytes())) return r;
   for (int J = 0; J < m; J += kSpNB) {
-    if (J > 0) {
-      const dim3 grid((unsigned)((m - J + kSpRows - 1) / kSpRows), (unsigned)N);
-      chol_step_update_kernel<<<grid, kSpThreads, chol_step_update_smem_bytes(), st>>>(prm, J);
+    const bool last = J + kSpNB >= m;
+    chol_step_diag_kernel<<<(unsigned)N, kSpThreads, chol_step_diag_smem_bytes(m), st>>>(prm, wk, J, last ? 1 : 0);
+    LAUNCH_CHECK();
+    if (!last) {
+      const dim3 grid((unsigned)((m - J - kSpNB + kSpRows - 1) / kSpRows), (unsigned)N);
+      chol_step_below_kernel<<<grid, kSpThreads, chol_step_below_smem_bytes(), st>>>(prm, wk, J);
       LAUNCH_CHECK();
     }
-    chol_step_factor_kernel<<<(unsigned)N, kSpThreads, chol_step_factor_smem_bytes(m), st>>>(prm, wk, J,
-                                                                                          J + kSpNB >= m ? 1 : 0);
-    LAUNCH_CHECK();
   }
   return 0;
 }
@@ -499,9 +501,8 @@ int run_chol(const double* mean, const double* y_exp, double* cov, const double*
   prm.n_notpd = n_notpd; prm.skip = skip; prm.notpd_value = notpd_value; prm.add_const = add_const;
   prm.N = N; prm.m = m;
   // Small matrices: warp-per-walker kernel, nine walkers resident per SM (their matrices stay in
-  // L2: 1332 x 8m^2 bytes <= ~64 MB).  Larger ones: CTA-per-walker, two per SM -- with more in
-  // flight the in-place factors fall out of L2 and every panel update re-reads them from HBM
-  // (measured at m = 300: 3.1 ms vs 1.6 ms per 1024 walkers).  GPBT_CHOL=warp|staged|cta overrides.
+  // L2: 1332 x 8m^2 bytes <= ~64 MB).  Larger ones: panel-synchronous kernels over the whole batch,
+  // or CTA-per-walker for small batches.  GPBT_CHOL=warp|batch|staged|cta overrides.
   const char* which = getenv("GPBT_CHOL");
   const size_t wsmem = chol_warp_smem_bytes(m);
   bool use_warp = m <= 80;
@@ -513,12 +514,13 @@ int run_chol(const double* mean, const double* y_exp, double* cov, const double*
     LAUNCH_CHECK();
     return 0;
   }
-  // stepped variant (GPBT_CHOL=batch, experimental): all walkers advance panel by panel, two launches
-  // per 32 columns.  Measured slower than the staged kernel at m = 300 (1.33 vs 1.14 ms per 1024
-  // walkers: its update launches run the tensor pipe at 60-75 %, but the ten factor launches cost
-  // 50-75 us each -- one warp per walker in a 32-pivot chain), so it is opt-in only.
+  // stepped variant: all walkers advance panel by panel (two launches per 32 columns).  Faster than the
+  // per-walker kernels once there are enough walkers to fill the machine per launch (measured at
+  // m = 300: 0.92 vs 0.96 ms at N = 512, 9.4 vs 11.2 ms at N = 8192); below that its 19 dependent
+  // launches cost more than one latency-bound kernel.  GPBT_CHOL=batch / staged / cta force a variant.
   const bool aligned_rows = (m % 2 == 0) && ((reinterpret_cast<uintptr_t>(cov) & 15) == 0);
-  if (aligned_rows && which && which[0] == 'b') return run_chol_stepped(prm, st);
+  const bool want_stepped = which ? which[0] == 'b' : N >= 256;
+  if (aligned_rows && want_stepped) return run_chol_stepped(prm, st);
   // staged kernel (operand stream through a cp.async ring): needs 16-byte aligned rows and its
   // fixed block assignment covers m <= 352
   const size_t ssmem = chol_staged_smem_bytes(m);
