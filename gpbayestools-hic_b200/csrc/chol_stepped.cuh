@@ -22,7 +22,6 @@
 namespace gpbt {
 
 constexpr int kSpNB = 32;       // panel width
-constexpr int kSpRows = 64;     // rows per `below` CTA (4 warps x 16)
 constexpr int kSpThreads = 128;
 constexpr int kSpKC = 16;       // operand columns per stage (two 8-column sub-blocks)
 constexpr int kSpStages = 3;
@@ -35,6 +34,43 @@ struct SteppedWork {
   double* tsq;      // [N]          |t|^2 so far
   int* bad;         // [N]          nonzero: a non-positive pivot was met
 };
+
+// One warp: OUT[16][16] (+)= sign * A[16][16] * B, all tiles in shared memory with row stride kSpLd.
+//   BT = true :  B(k, n) = Bm[n][k]   (OUT = A Bm^T)        BT = false:  B(k, n) = Bm[k][n]   (OUT = A Bm)
+// `init` (may be null) is the starting value of OUT.  Lane (g, t) owns OUT[8mb + g][8nb + 2t .. +1].
+template <bool BT>
+__device__ __forceinline__ void tile16_mma(const double* A, const double* Bm, const double* init, double* OUT,
+                                           double sign, int g, int t) {
+  double acc[2][2][2];
+#pragma unroll
+  for (int mb = 0; mb < 2; mb++)
+#pragma unroll
+    for (int nb2 = 0; nb2 < 2; nb2++) {
+      acc[mb][nb2][0] = init ? init[(8 * mb + g) * kSpLd + 8 * nb2 + 2 * t] : 0.0;
+      acc[mb][nb2][1] = init ? init[(8 * mb + g) * kSpLd + 8 * nb2 + 2 * t + 1] : 0.0;
+    }
+#pragma unroll
+  for (int s = 0; s < 4; s++) {
+    double a[2], b[2];
+#pragma unroll
+    for (int mb = 0; mb < 2; mb++) a[mb] = sign * A[(8 * mb + g) * kSpLd + 4 * s + t];
+#pragma unroll
+    for (int nb2 = 0; nb2 < 2; nb2++)
+      b[nb2] = BT ? Bm[(8 * nb2 + g) * kSpLd + 4 * s + t] : Bm[(4 * s + t) * kSpLd + 8 * nb2 + g];
+#pragma unroll
+    for (int mb = 0; mb < 2; mb++)
+#pragma unroll
+      for (int nb2 = 0; nb2 < 2; nb2++) dmma884(acc[mb][nb2][0], acc[mb][nb2][1], a[mb], b[nb2]);
+  }
+  __syncwarp();   // OUT may alias an operand: everybody has read before anybody writes
+#pragma unroll
+  for (int mb = 0; mb < 2; mb++)
+#pragma unroll
+    for (int nb2 = 0; nb2 < 2; nb2++)
+      *reinterpret_cast<double2*>(&OUT[(8 * mb + g) * kSpLd + 8 * nb2 + 2 * t]) =
+          make_double2(acc[mb][nb2][0], acc[mb][nb2][1]);
+  __syncwarp();
+}
 
 // ---- diag ------------------------------------------------------------------------------------------
 constexpr int kSpDiagStages = 6;   // the diagonal update is a short, latency-bound stream: prefetch deep
@@ -148,39 +184,15 @@ __global__ void __launch_bounds__(kSpThreads) chol_step_diag_kernel(const CholPa
     //      (a monolithic 32-pivot version is ~12 k instructions of straight-line code per warp and was
     //      measured 4x slower: it does not fit the instruction cache)
     bool pd = true;
-    const int r = lane & 15, hc = (lane >> 4) * 8;   // products: lane = row r, columns hc .. hc+7
+    const int r = lane & 15;
     double lsum = 0.0;
 #pragma unroll 1
     for (int blk = 0; blk < 2; blk++) {
       const int o = 16 * blk;
       if (blk == 1) {
-        // L21 = D21 I11^T (I11 lower: k <= c), then D22 -= L21 L21^T
-        double l21[8];
-#pragma unroll
-        for (int cc = 0; cc < 8; cc++) {
-          const int c = hc + cc;
-          double sacc = 0.0;
-#pragma unroll
-          for (int k = 0; k < 16; k++)   // (I11 is stored with explicit zeros above its diagonal)
-            sacc = fma(D[(16 + r) * kSpLd + k], Dinv[c * kSpLd + k], sacc);
-          l21[cc] = sacc;
-        }
-        __syncwarp();
-#pragma unroll
-        for (int cc = 0; cc < 8; cc++) D[(16 + r) * kSpLd + hc + cc] = l21[cc];
-        __syncwarp();
-#pragma unroll
-        for (int cc = 0; cc < 8; cc++) {
-          const int c = hc + cc;
-          double sacc = D[(16 + r) * kSpLd + 16 + c];
-#pragma unroll
-          for (int k = 0; k < 16; k++) sacc = fma(-D[(16 + r) * kSpLd + k], D[(16 + c) * kSpLd + k], sacc);
-          l21[cc] = sacc;
-        }
-        __syncwarp();
-#pragma unroll
-        for (int cc = 0; cc < 8; cc++) D[(16 + r) * kSpLd + 16 + hc + cc] = l21[cc];
-        __syncwarp();
+        // L21 = D21 I11^T, then D22 -= L21 L21^T  (16x16x16 products on the tensor pipe)
+        tile16_mma<true>(D + 16 * kSpLd, Dinv, nullptr, D + 16 * kSpLd, 1.0, g, t);
+        tile16_mma<true>(D + 16 * kSpLd, D + 16 * kSpLd, D + 16 * kSpLd + 16, D + 16 * kSpLd + 16, -1.0, g, t);
       }
       double S[16];
 #pragma unroll
@@ -214,37 +226,13 @@ __global__ void __launch_bounds__(kSpThreads) chol_step_diag_kernel(const CholPa
     if (!pd && lane == 0) s_bad = 1;
     lsum = warp_sum(lsum);
     if (lane == 0) wk.logdet[w] = (J == 0 ? 0.0 : wk.logdet[w]) + lsum;
-    // the upper-right block of the factor is zero; Dinv21 = -I22 (L21 I11), through the (still unused)
-    // upper-right block of Dinv as scratch
-    {
-      double mrow[8];
-#pragma unroll
-      for (int cc = 0; cc < 8; cc++) {
-        const int c = hc + cc;
-        double sacc = 0.0;
-#pragma unroll
-        for (int k = 0; k < 16; k++) sacc = fma(D[(16 + r) * kSpLd + k], Dinv[k * kSpLd + c], sacc);   // zeros for k < c
-        mrow[cc] = sacc;   // M[r][c] = (L21 I11)[r][c]
-      }
-#pragma unroll
-      for (int cc = 0; cc < 8; cc++) Dinv[r * kSpLd + 16 + hc + cc] = mrow[cc];   // scratch: M[r][c] at [r][16 + c]
-      __syncwarp();
-#pragma unroll
-      for (int cc = 0; cc < 8; cc++) {
-        const int c = hc + cc;
-        double sacc = 0.0;
-#pragma unroll
-        for (int k = 0; k < 16; k++)   // (I22 has explicit zeros above its diagonal)
-          sacc = fma(-Dinv[(16 + r) * kSpLd + 16 + k], Dinv[k * kSpLd + 16 + c], sacc);
-        mrow[cc] = sacc;
-      }
-      __syncwarp();
-#pragma unroll
-      for (int cc = 0; cc < 8; cc++) {
-        Dinv[(16 + r) * kSpLd + hc + cc] = mrow[cc];
-        Dinv[r * kSpLd + 16 + hc + cc] = 0.0;
-        D[r * kSpLd + 16 + hc + cc] = 0.0;
-      }
+    // Dinv21 = -I22 (L21 I11), through the (still unused) upper-right block of Dinv as scratch; the
+    // upper-right blocks of the factor and of its inverse are zero
+    tile16_mma<false>(D + 16 * kSpLd, Dinv, nullptr, Dinv + 16, 1.0, g, t);                      // M = L21 I11
+    tile16_mma<false>(Dinv + 16 * kSpLd + 16, Dinv + 16, nullptr, Dinv + 16 * kSpLd, -1.0, g, t);  // -I22 M
+    for (int idx = lane; idx < 256; idx += 32) {
+      Dinv[(idx >> 4) * kSpLd + 16 + (idx & 15)] = 0.0;
+      D[(idx >> 4) * kSpLd + 16 + (idx & 15)] = 0.0;
     }
   }
   __syncthreads();
@@ -282,22 +270,28 @@ __global__ void __launch_bounds__(kSpThreads) chol_step_diag_kernel(const CholPa
 }
 
 // ---- below -----------------------------------------------------------------------------------------
+// MB = m8 row blocks per warp: a CTA covers 32 MB rows.  64-row tiles amortise the B-operand loads best;
+// 32-row tiles are used for the panels where they cut the padding of the row range (e.g. 76 rows left:
+// 96 instead of 128 computed).
+template <int MB>
 constexpr size_t chol_step_below_smem_bytes() {
   // the operand ring (the finished tile is parked over it for the triangular solve) + Dinv
-  return sizeof(double) * ((size_t)kSpStages * 2 * (kSpRows + kSpNB) * 8 + (size_t)kSpNB * kSpLd);
+  return sizeof(double) * ((size_t)kSpStages * 2 * (32 * MB + kSpNB) * 8 + (size_t)kSpNB * kSpLd);
 }
 
+template <int MB>
 __global__ void __launch_bounds__(kSpThreads) chol_step_below_kernel(const CholParams prm, const SteppedWork wk, int J) {
+  constexpr int kRows = 32 * MB;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* ring = reinterpret_cast<double*>(smem_raw);   // [stages][ A: [2][64][8] | B: [2][32][8] ]
-  constexpr int kStage = 2 * (kSpRows + kSpNB) * 8;
+  constexpr int kStage = 2 * (kRows + kSpNB) * 8;
   double* Dv = ring + (size_t)kSpStages * kStage;        // [32][kSpLd] Dinv of this walker
-  double* T = ring;                                      // [64][kSpLd] the tile, after the stream is done
-  static_assert(kSpRows * kSpLd <= kSpStages * kStage, "tile must fit over the ring");
+  double* T = ring;                                      // [kRows][kSpLd] the tile, after the stream is done
+  static_assert(kRows * kSpLd <= kSpStages * kStage, "tile must fit over the ring");
   const int m = prm.m;
   const int64_t w = blockIdx.y;
   if (prm.skip != nullptr && prm.skip[w]) return;
-  const int row0 = J + kSpNB + blockIdx.x * kSpRows;
+  const int row0 = J + kSpNB + blockIdx.x * kRows;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   double* Lw = prm.cov + (size_t)w * m * m;
@@ -315,11 +309,11 @@ __global__ void __launch_bounds__(kSpThreads) chol_step_below_kernel(const CholP
   auto issue = [&](int s) {
     if (s < nst) {
       double* A = ring + (size_t)(s % kSpStages) * kStage;
-      double* B = A + 2 * kSpRows * 8;
+      double* B = A + 2 * kRows * 8;
       const int k0 = s * kSpKC;
-      for (int idx = tid; idx < kSpRows * 8; idx += kSpThreads) {
+      for (int idx = tid; idx < kRows * 8; idx += kSpThreads) {
         const int r = idx >> 3, q8 = idx & 7, sub = q8 >> 2, q4 = q8 & 3;
-        cp_async16(A + ((size_t)sub * kSpRows + r) * 8 + 2 * q4,
+        cp_async16(A + ((size_t)sub * kRows + r) * 8 + 2 * q4,
                    Lw + (size_t)min(row0 + r, m - 1) * m + k0 + 8 * sub + 2 * q4);
       }
       for (int idx = tid; idx < kSpNB * 8; idx += kSpThreads) {
@@ -333,10 +327,10 @@ __global__ void __launch_bounds__(kSpThreads) chol_step_below_kernel(const CholP
   issue(1);
 
   // the C tile goes straight into the accumulators (these loads overlap the first stages)
-  double acc[2][4][2];
+  double acc[MB][4][2];
 #pragma unroll
-  for (int mb = 0; mb < 2; mb++) {
-    const int r = min(row0 + 16 * warp + 8 * mb + g, m - 1);
+  for (int mb = 0; mb < MB; mb++) {
+    const int r = min(row0 + 8 * MB * warp + 8 * mb + g, m - 1);
 #pragma unroll
     for (int nbk = 0; nbk < 4; nbk++) {
       const double2 v = *reinterpret_cast<const double2*>(Lw + (size_t)r * m + J + 8 * nbk + 2 * t);
@@ -350,19 +344,19 @@ __global__ void __launch_bounds__(kSpThreads) chol_step_below_kernel(const CholP
     __syncthreads();
     issue(s + 2);
     const double* A = ring + (size_t)(s % kSpStages) * kStage;
-    const double* B = A + 2 * kSpRows * 8;
+    const double* B = A + 2 * kRows * 8;
 #pragma unroll
     for (int sub = 0; sub < 2; sub++) {
       // logical k slot t of step {0,1} is the sub-block column 2t + {0,1} (same permutation for A and B)
-      double2 b[4], a[2];
+      double2 b[4], a[MB];
 #pragma unroll
       for (int nbk = 0; nbk < 4; nbk++)
         b[nbk] = *reinterpret_cast<const double2*>(B + ((size_t)sub * kSpNB + 8 * nbk + g) * 8 + 2 * t);
 #pragma unroll
-      for (int mb = 0; mb < 2; mb++)
-        a[mb] = *reinterpret_cast<const double2*>(A + ((size_t)sub * kSpRows + 16 * warp + 8 * mb + g) * 8 + 2 * t);
+      for (int mb = 0; mb < MB; mb++)
+        a[mb] = *reinterpret_cast<const double2*>(A + ((size_t)sub * kRows + 8 * MB * warp + 8 * mb + g) * 8 + 2 * t);
 #pragma unroll
-      for (int mb = 0; mb < 2; mb++)
+      for (int mb = 0; mb < MB; mb++)
 #pragma unroll
         for (int nbk = 0; nbk < 4; nbk++) {
           dmma884(acc[mb][nbk][0], acc[mb][nbk][1], -a[mb].x, b[nbk].x);
@@ -374,18 +368,18 @@ __global__ void __launch_bounds__(kSpThreads) chol_step_below_kernel(const CholP
   __syncthreads();   // every warp is done with the ring; Dinv has landed
   // park the updated tile, then rows <- rows * Dinv^T (each warp reads back only its own 16 rows)
 #pragma unroll
-  for (int mb = 0; mb < 2; mb++)
+  for (int mb = 0; mb < MB; mb++)
 #pragma unroll
     for (int nbk = 0; nbk < 4; nbk++)
-      *reinterpret_cast<double2*>(&T[(16 * warp + 8 * mb + g) * kSpLd + 8 * nbk + 2 * t]) =
+      *reinterpret_cast<double2*>(&T[(8 * MB * warp + 8 * mb + g) * kSpLd + 8 * nbk + 2 * t]) =
           make_double2(acc[mb][nbk][0], acc[mb][nbk][1]);
   __syncwarp();
 #pragma unroll
-  for (int mb = 0; mb < 2; mb++) {
+  for (int mb = 0; mb < MB; mb++) {
     double2 a[4];
 #pragma unroll
     for (int kk = 0; kk < 4; kk++)
-      a[kk] = *reinterpret_cast<const double2*>(&T[(16 * warp + 8 * mb + g) * kSpLd + 8 * kk + 2 * t]);
+      a[kk] = *reinterpret_cast<const double2*>(&T[(8 * MB * warp + 8 * mb + g) * kSpLd + 8 * kk + 2 * t]);
     double acc2[4][2];
 #pragma unroll
     for (int nbk = 0; nbk < 4; nbk++) acc2[nbk][0] = acc2[nbk][1] = 0.0;
@@ -397,7 +391,7 @@ __global__ void __launch_bounds__(kSpThreads) chol_step_below_kernel(const CholP
         dmma884(acc2[nbk][0], acc2[nbk][1], a[kk].x, b.x);
         dmma884(acc2[nbk][0], acc2[nbk][1], a[kk].y, b.y);
       }
-    const int r = row0 + 16 * warp + 8 * mb + g;
+    const int r = row0 + 8 * MB * warp + 8 * mb + g;
     if (r < m) {
 #pragma unroll
       for (int nbk = 0; nbk < 4; nbk++)

@@ -478,14 +478,22 @@ int run_chol_stepped(const CholParams& prm, cudaStream_t st) {
     LAUNCH_CHECK();
   }
   if (int r = ensure_dynamic_smem<chol_step_diag_kernel>(chol_step_diag_smem_bytes(m))) return r;
-  if (int r = ensure_dynamic_smem<chol_step_below_kernel>(chol_step_below_smem_bytes())) return r;
+  if (int r = ensure_dynamic_smem<chol_step_below_kernel<2>>(chol_step_below_smem_bytes<2>())) return r;
+  if (int r = ensure_dynamic_smem<chol_step_below_kernel<1>>(chol_step_below_smem_bytes<1>())) return r;
   for (int J = 0; J < m; J += kSpNB) {
     const bool last = J + kSpNB >= m;
     chol_step_diag_kernel<<<(unsigned)N, kSpThreads, chol_step_diag_smem_bytes(m), st>>>(prm, wk, J, last ? 1 : 0);
     LAUNCH_CHECK();
     if (!last) {
-      const dim3 grid((unsigned)((m - J - kSpNB + kSpRows - 1) / kSpRows), (unsigned)N);
-      chol_step_below_kernel<<<grid, kSpThreads, chol_step_below_smem_bytes(), st>>>(prm, wk, J);
+      // 64-row tiles, or 32-row tiles where that trims the padded part of the row range
+      const int rows = m - J - kSpNB;
+      if ((rows + 31) / 32 * 32 < (rows + 63) / 64 * 64) {
+        const dim3 grid((unsigned)((rows + 31) / 32), (unsigned)N);
+        chol_step_below_kernel<1><<<grid, kSpThreads, chol_step_below_smem_bytes<1>(), st>>>(prm, wk, J);
+      } else {
+        const dim3 grid((unsigned)((rows + 63) / 64), (unsigned)N);
+        chol_step_below_kernel<2><<<grid, kSpThreads, chol_step_below_smem_bytes<2>(), st>>>(prm, wk, J);
+      }
       LAUNCH_CHECK();
     }
   }
