@@ -6,7 +6,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/gpbt.h"
@@ -445,27 +448,43 @@ int run_backtransform(gpbt_emulator_t e, const double* zm, const double* zv, int
   return 0;
 }
 
-// work vectors of the stepped Cholesky (t, log-determinant, non-PD flag per walker), one set per device
+// Work vectors of the stepped Cholesky (Dinv, t, log-determinant, |t|^2, non-PD flag per walker): one
+// grow-only buffer per (device, stream) -- calls on different streams may overlap on the GPU, calls on
+// one stream cannot.
 struct SteppedCache {
   double* buf = nullptr;
   size_t bytes = 0;
 };
-SteppedCache g_stepped[kMaxDevices];
+std::map<std::pair<int, cudaStream_t>, SteppedCache> g_stepped;
+std::mutex g_stepped_mutex;
+
+void release_stepped_buffer(int device, cudaStream_t st) {
+  std::lock_guard<std::mutex> lock(g_stepped_mutex);
+  auto it = g_stepped.find(std::make_pair(device, st));
+  if (it == g_stepped.end()) return;
+  if (it->second.buf) cudaFree(it->second.buf);
+  g_stepped.erase(it);
+}
 
 int run_chol_stepped(const CholParams& prm, cudaStream_t st) {
   const int m = prm.m;
   const int64_t N = prm.N;
-  const int dev = current_device();
-  if (dev < 0 || dev >= kMaxDevices) return fail(GPBT_EINVAL, "device index %d out of range", dev);
   const size_t need = (size_t)N * ((size_t)m + kSpNB * kSpNB + 3) * sizeof(double);
-  SteppedCache& c = g_stepped[dev];
-  if (need > c.bytes) {
-    if (c.buf) cudaFree(c.buf);
-    c.buf = nullptr;
-    c.bytes = 0;
-    CU(cudaMalloc(&c.buf, need));
-    c.bytes = need;
-    g_ws_generation++;
+  SteppedCache c;
+  {
+    std::lock_guard<std::mutex> lock(g_stepped_mutex);
+    SteppedCache& slot = g_stepped[std::make_pair(current_device(), st)];
+    if (need > slot.bytes) {
+      // (work of earlier calls on this stream that still uses the old buffer has been enqueued before this
+      // free; cudaFree synchronises the device)
+      if (slot.buf) cudaFree(slot.buf);
+      slot.buf = nullptr;
+      slot.bytes = 0;
+      CU(cudaMalloc(&slot.buf, need));
+      slot.bytes = need;
+      g_ws_generation++;
+    }
+    c = slot;
   }
   SteppedWork wk;
   wk.dinv = c.buf;                                  // first: 16-byte aligned rows for cp.async
@@ -800,8 +819,13 @@ int chain_build(gpbt_chain* ch, const gpbt_emulator_t* emus, int n_emu, int p, c
 }
 }  // namespace
 
+namespace {
+void release_stepped_buffer(int device, cudaStream_t st);   // defined next to run_chol_stepped
+}
+
 extern "C" int gpbt_chain_destroy(gpbt_chain_t ch) {
   if (!ch) return 0;
+  if (ch->stream) release_stepped_buffer(ch->device, ch->stream);
   for (double* d : ch->R_blocks) cudaFree(d);
   for (double* d : ch->base_like) cudaFree(d);
   if (ch->zc_x_host) cudaFreeHost(ch->zc_x_host);
