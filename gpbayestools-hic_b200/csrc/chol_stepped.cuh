@@ -3,12 +3,13 @@
 // (chol_staged.cuh: latency bound, two walkers per SM, FP64 pipe 29 % busy).
 //
 //   diag J    grid (walkers), 4 warps: the 32x32 diagonal block  D = C[J:J+32, J:J+32] - L[J:J+32, :J] L[..]^T
-//             (DMMA over a cp.async ring), factorised in registers by warp 0 (lane = row, pivots and
-//             multipliers by shuffle), its inverse by forward substitution (lane = column of the
-//             identity); meanwhile warps 1-3 form the right-hand side of the forward solve.  Writes the
-//             factor in place, Dinv to a work buffer, t[J:J+32] = Dinv (y - L[J:J+32, :J] t[:J]),
-//             accumulates log-determinant and |t|^2; the last panel's launch emits lp[w].
-//   below J   grid (64-row tiles below the block, walkers):
+//             by DMMA over a 6-stage cp.async ring; the right-hand side of the forward solve,
+//             y[J:J+32] - L[J:J+32, :J] t[:J], rides on the same operand stream.  Warp 0 then factorises
+//             the block as two 16x16 register factorisations (lanes 0-15: rows, pivots and multipliers
+//             by shuffle; lanes 16-31: identity rows that come out as the inverse) around four
+//             16x16x16 products on the tensor pipe.  Writes the factor in place, Dinv to a work buffer,
+//             t[J:J+32] = Dinv rhs, accumulates log-determinant and |t|^2; the last panel emits lp[w].
+//   below J   grid (64- or 32-row tiles below the block, walkers):
 //             rows <- (C[rows, J:J+32] - L[rows, :J] L[J:J+32, :J]^T) Dinv^T.
 //             The C tile is loaded straight into the accumulators before the operand stream starts
 //             (one memory round trip per CTA, not two), the product runs with a negated A fragment, and
