@@ -526,7 +526,7 @@ def test_random_shapes_vs_oracle(shape):
     ch.release()
 
 
-@pytest.mark.parametrize("m", [96, 130, 300])
+@pytest.mark.parametrize("m", [96, 130, 300, 602])
 def test_cholesky_variants_agree(m, monkeypatch):
     """gpbt_mvn_loglike through each Cholesky kernel that takes this size (staged default, register-fed
     CTA kernel, warp-per-walker, and the opt-in stepped variant that advances all walkers panel by
