@@ -458,6 +458,22 @@ struct SteppedCache {
 std::map<std::pair<int, cudaStream_t>, SteppedCache> g_stepped;
 std::mutex g_stepped_mutex;
 
+// launch with programmatic stream serialisation (see chol_stepped.cuh)
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, unsigned threads, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 void release_stepped_buffer(int device, cudaStream_t st) {
   std::lock_guard<std::mutex> lock(g_stepped_mutex);
   auto it = g_stepped.find(std::make_pair(device, st));
@@ -501,17 +517,18 @@ int run_chol_stepped(const CholParams& prm, cudaStream_t st) {
   if (int r = ensure_dynamic_smem<chol_step_below_kernel<1>>(chol_step_below_smem_bytes<1>())) return r;
   for (int J = 0; J < m; J += kSpNB) {
     const bool last = J + kSpNB >= m;
-    chol_step_diag_kernel<<<(unsigned)N, kSpThreads, chol_step_diag_smem_bytes(m), st>>>(prm, wk, J, last ? 1 : 0);
+    CU(launch_pdl(chol_step_diag_kernel, dim3((unsigned)N), kSpThreads, chol_step_diag_smem_bytes(m), st, prm, wk, J,
+                  last ? 1 : 0));
     LAUNCH_CHECK();
     if (!last) {
       // 64-row tiles, or 32-row tiles where that trims the padded part of the row range
       const int rows = m - J - kSpNB;
       if ((rows + 31) / 32 * 32 < (rows + 63) / 64 * 64) {
         const dim3 grid((unsigned)((rows + 31) / 32), (unsigned)N);
-        chol_step_below_kernel<1><<<grid, kSpThreads, chol_step_below_smem_bytes<1>(), st>>>(prm, wk, J);
+        CU(launch_pdl(chol_step_below_kernel<1>, grid, kSpThreads, chol_step_below_smem_bytes<1>(), st, prm, wk, J));
       } else {
         const dim3 grid((unsigned)((rows + 63) / 64), (unsigned)N);
-        chol_step_below_kernel<2><<<grid, kSpThreads, chol_step_below_smem_bytes<2>(), st>>>(prm, wk, J);
+        CU(launch_pdl(chol_step_below_kernel<2>, grid, kSpThreads, chol_step_below_smem_bytes<2>(), st, prm, wk, J));
       }
       LAUNCH_CHECK();
     }

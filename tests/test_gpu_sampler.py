@@ -275,3 +275,38 @@ def test_ensemble_size_boundaries(c1, nw):
     np.testing.assert_array_equal(s.get_chain(), chain)
     np.testing.assert_array_equal(s.n_accepted, acc)
     s.close()
+
+
+def test_graph_replay_over_the_stepped_cholesky():
+    """A chain without low-rank factors (dense path) with m > 80 and half-ensembles of 256+ walkers runs
+    the panel-synchronous Cholesky (19+ dependent launches with programmatic dependent launch) inside the
+    captured step: graph replay and eager launches must give the same chain, and both the oracle's."""
+    from gpbt_b200 import synthetic
+    from gpbt_b200.device import DeviceChain
+    from gpbt_b200.sampler import DeviceEnsembleSampler
+    from gpbt_b200.state import EmulatorState
+    arr = synthetic.untrained_state_arrays(4, 40, 96, 5)
+    st = EmulatorState.from_arrays(**arr, keep_L=True)
+    od = st.oracle_dict()
+    lo, hi = synthetic.box(4)
+    y = orc.emulator_predict(od, (0.5 * (lo + hi))[None, :], False)[0]
+    cov_exp = np.diag((0.05 * np.abs(y)) ** 2 + 1e-3)
+    dc = DeviceChain([st], lo, hi, y, cov_exp, lowrank=False)
+    logp = lambda X: orc.log_posterior([od], X, lo, hi, y, cov_exp)
+    nw, steps, seed = 600, 3, 11
+    rng = np.random.default_rng(1)
+    x0 = 0.5 * (lo + hi) + 0.3 * (hi - lo) * rng.uniform(-1, 1, (nw, 4))
+    out = []
+    for use_graph in (True, False):
+        s = DeviceEnsembleSampler(nw, 4, dc, seed=seed, use_graph=use_graph)
+        s.set_state(x0)
+        s.advance(steps)
+        out.append((s.get_chain(), s.get_log_prob()))
+        s.close()
+    np.testing.assert_array_equal(out[0][0], out[1][0])
+    np.testing.assert_array_equal(out[0][1], out[1][1])
+    u, partner, perm = eo.philox_streams(seed, 0, steps, nw)
+    chain, lps, _ = eo.stretch_run(logp, x0, logp(x0), u, partner, perm)
+    np.testing.assert_array_equal(out[0][0], chain)
+    assert np.max(np.abs(out[0][1] - lps)) <= ABS_LP
+    dc.release()
