@@ -28,12 +28,6 @@ constexpr int kSpKC = 16;       // operand columns per stage (two 8-column sub-b
 constexpr int kSpStages = 3;
 constexpr int kSpLd = 34;       // row stride of 32-column tiles in shared memory (16-byte rows)
 
-// Programmatic dependent launch: the next launch of the chain is scheduled while this one drains (its
-// CTAs sit at the wait until this grid has completed and its writes are visible), which hides the launch
-// latency and the ramp-up of 19 dependent launches.  Both are no-ops without the launch attribute.
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
-__device__ __forceinline__ void pdl_wait_prior_grids() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
 struct SteppedWork {
   double* tvec;     // [N, m]       forward-solve vector t = L^-1 y
   double* dinv;     // [N, 32, 32]  inverse of the current diagonal block's factor (lower)

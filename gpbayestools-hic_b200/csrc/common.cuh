@@ -31,4 +31,12 @@ __host__ __device__ __forceinline__ int64_t round_up(int64_t x, int64_t a) {
   return (x + a - 1) / a * a;
 }
 
+// Programmatic dependent launch (griddepcontrol): a kernel launched with the programmatic-stream-
+// serialisation attribute is scheduled while its predecessor drains; its CTAs sit at the wait until the
+// predecessor grid has completed and its writes are visible.  Hides launch latency and ramp-up along
+// chains of small dependent launches.  Both instructions are no-ops without the launch attribute; a
+// kernel launched WITH the attribute must execute the wait before it touches anything a predecessor wrote.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait_prior_grids() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 }  // namespace gpbt

@@ -290,12 +290,16 @@ constexpr int kEnsembleFusedMaxWalkers = 2048;
 
 __global__ void __launch_bounds__(1024) ensemble_begin_kernel(const EnsembleBuffers b) {
   extern __shared__ unsigned long long keys[];
+  pdl_launch_dependents();
+  pdl_wait_prior_grids();
   split_walkers(b.ctl, b.seed, b.nw, b.randomize, b.perm, keys, threadIdx.x, blockDim.x);
   __syncthreads();   // perm (global) is read by other threads of this CTA below
   for (int i = threadIdx.x; i < active_size(b.nw, 0); i += blockDim.x) propose_one(b, 0, i);
 }
 
 __global__ void __launch_bounds__(1024) ensemble_mid_kernel(const EnsembleBuffers b) {
+  pdl_launch_dependents();
+  pdl_wait_prior_grids();
   if (threadIdx.x == 0) fold_notpd(b);
   for (int i = threadIdx.x; i < active_size(b.nw, 0); i += blockDim.x) accept_one(b, 0, i);
   __syncthreads();   // the second set draws partners from the updated first set
@@ -303,6 +307,8 @@ __global__ void __launch_bounds__(1024) ensemble_mid_kernel(const EnsembleBuffer
 }
 
 __global__ void __launch_bounds__(1024) ensemble_end_kernel(const EnsembleBuffers b, EnsembleCtl* ctl) {
+  pdl_launch_dependents();
+  pdl_wait_prior_grids();
   if (threadIdx.x == 0) fold_notpd(b);
   for (int i = threadIdx.x; i < active_size(b.nw, 1); i += blockDim.x) accept_one(b, 1, i);
   __syncthreads();

@@ -107,6 +107,23 @@ int ensure_dynamic_smem(size_t bytes) {
   return 0;
 }
 
+// launch with programmatic stream serialisation (see common.cuh); only for kernels that execute
+// pdl_wait_prior_grids() before they touch a predecessor's output
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, unsigned threads, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 }  // namespace
 
 struct gpbt_emulator {
@@ -344,7 +361,7 @@ int launch_pc_predict(const PcPredictParams& prm, cudaStream_t st) {
   const size_t smem = pc_predict_smem_bytes<TW>(prm.n_pad, prm.p_pad);
   if (int r = ensure_dynamic_smem<pc_predict_kernel<TW, KIND, P2>>(smem)) return r;
   dim3 grid((unsigned)((prm.N + TW - 1) / TW), (unsigned)prm.q);
-  pc_predict_kernel<TW, KIND, P2><<<grid, kPcThreads, smem, st>>>(prm);
+  CU(launch_pdl(pc_predict_kernel<TW, KIND, P2>, grid, kPcThreads, smem, st, prm));
   LAUNCH_CHECK();
   return 0;
 }
@@ -457,22 +474,6 @@ struct SteppedCache {
 };
 std::map<std::pair<int, cudaStream_t>, SteppedCache> g_stepped;
 std::mutex g_stepped_mutex;
-
-// launch with programmatic stream serialisation (see chol_stepped.cuh)
-template <typename... KArgs, typename... Args>
-cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, unsigned threads, size_t smem, cudaStream_t st, Args... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = dim3(threads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
-}
 
 void release_stepped_buffer(int device, cudaStream_t st) {
   std::lock_guard<std::mutex> lock(g_stepped_mutex);
@@ -1026,7 +1027,8 @@ int log_posterior_impl(gpbt_chain_t ch, const double* X, double oob_value, doubl
       const unsigned grid = (unsigned)((N + kLrWarps - 1) / kLrWarps);
       if (qb <= 32 && !getenv("GPBT_LOWRANK_GENERIC")) {
         switch ((qb + 3) / 4) {
-#define GPBT_Q(QP) case QP / 4: lowrank_loglike_reg_kernel<QP><<<grid, kLrWarps * 32, 0, st>>>(prm); break;
+#define GPBT_Q(QP) \
+  case QP / 4: CU(launch_pdl(lowrank_loglike_reg_kernel<QP>, dim3(grid), kLrWarps * 32, 0, st, prm)); break;
           GPBT_Q(4) GPBT_Q(8) GPBT_Q(12) GPBT_Q(16) GPBT_Q(20) GPBT_Q(24) GPBT_Q(28) GPBT_Q(32)
 #undef GPBT_Q
         }
@@ -1036,7 +1038,7 @@ int log_posterior_impl(gpbt_chain_t ch, const double* X, double oob_value, doubl
       const size_t smem = lowrank_smem_bytes(qb);
       if (smem > (size_t)max_optin_smem()) return fail(GPBT_ESHAPE, "low-rank path: Q = %d too large", qb);
       if (int r = ensure_dynamic_smem<lowrank_loglike_kernel>(smem)) return r;
-      lowrank_loglike_kernel<<<grid, kLrWarps * 32, smem, st>>>(prm);
+      CU(launch_pdl(lowrank_loglike_kernel, dim3(grid), kLrWarps * 32, smem, st, prm));
       LAUNCH_CHECK();
     }
     return 0;
@@ -1176,14 +1178,14 @@ int ensemble_enqueue_step(gpbt_ensemble* en, cudaStream_t st) {
   const size_t key_bytes = (size_t)nw * sizeof(unsigned long long);
   if (nw <= kEnsembleFusedMaxWalkers && !getenv("GPBT_ENSEMBLE_SPLIT_KERNELS")) {
     // small ensemble: launch latency is the cost, three single-CTA kernels around the two calls
-    ensemble_begin_kernel<<<1, 1024, key_bytes, st>>>(b);
+    CU(launch_pdl(ensemble_begin_kernel, dim3(1), 1024, key_bytes, st, b));
     LAUNCH_CHECK();
     if (int r = ensemble_log_posterior(en, en->n_half, st)) return r;
-    ensemble_mid_kernel<<<1, 1024, 0, st>>>(b);
+    CU(launch_pdl(ensemble_mid_kernel, dim3(1), 1024, 0, st, b));
     LAUNCH_CHECK();
     if (nw - en->n_half > 0)
       if (int r = ensemble_log_posterior(en, nw - en->n_half, st)) return r;
-    ensemble_end_kernel<<<1, 1024, 0, st>>>(b, en->ctl);
+    CU(launch_pdl(ensemble_end_kernel, dim3(1), 1024, 0, st, b, en->ctl));
     LAUNCH_CHECK();
     return 0;
   }

@@ -73,6 +73,8 @@ inline size_t lowrank_smem_bytes(int Q) {
 // and the loops over columns are warp-uniform.
 __global__ void __launch_bounds__(kLrWarps * 32) lowrank_loglike_kernel(const LowrankParams prm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  pdl_launch_dependents();
+  pdl_wait_prior_grids();
   const int Q = prm.Q, ld = lowrank_stride(Q);
   double* Rt = reinterpret_cast<double*>(smem_raw);  // Rt[k * ld + a] = R[a][k]   (zero for k < a)
   double* Rr = Rt + (size_t)Q * ld;                  // Rr[a * ld + k] = R[a][k]   (row-major, broadcast reads)
@@ -173,6 +175,8 @@ __global__ void __launch_bounds__(kLrWarps * 32) lowrank_loglike_reg_kernel(cons
   constexpr int LD = QP + 2;                 // even stride (16-byte row alignment), conflict-light
   __shared__ __align__(16) double Rr[QP * LD];            // R row-major, zero below the diagonal
   __shared__ __align__(16) double zv[kLrWarps][2 * QP];   // per warp: z[QP], v[QP]
+  pdl_launch_dependents();
+  pdl_wait_prior_grids();
   const int Q = prm.Q;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < QP * LD; i += blockDim.x) {

@@ -155,6 +155,10 @@ __global__ void __launch_bounds__(kPcThreads, TW == 16 ? 2 : 1) pc_predict_kerne
       tma_bulk_g2s(xst + (size_t)c * kXsRows * xrow, Xs_j + (size_t)c * kXsRows * xrow, chunk_bytes(c), &bars[c]);
     }
   }
+  // (the design is constant: its first TMA copies are in flight before this kernel waits for whoever
+  // produced X -- a sampler's proposal kernel, the parameter pre-transform)
+  pdl_launch_dependents();
+  pdl_wait_prior_grids();
   // ---- the scaled walker tile: xs[d/2][w] = (x_d, x_d+1) / ell_j (true division, as sklearn's
   //      X / length_scale) ------------------------------------------------------------------
   for (int idx = tid; idx < p_pad * TW; idx += kPcThreads) {
