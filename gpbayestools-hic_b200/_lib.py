@@ -23,6 +23,8 @@ SYMBOLS = [
     "gpbt_host_temp_exchange", "gpbt_ensemble_create", "gpbt_ensemble_destroy", "gpbt_ensemble_set_state", "gpbt_ensemble_get_state",
     "gpbt_ensemble_run", "gpbt_ensemble_steps", "gpbt_ensemble_reserve",
     "gpbt_ensemble_prepare", "gpbt_ensemble_begin_half", "gpbt_ensemble_copy_proposals", "gpbt_ensemble_end_half", "gpbt_ensemble_read", "gpbt_ensemble_reset",
+    "gpbt_device_count", "gpbt_set_device", "gpbt_get_device", "gpbt_set_option",
+    "gpbt_fanout_create", "gpbt_fanout_destroy", "gpbt_fanout_size", "gpbt_fanout_log_posterior_host",
 ]
 
 
@@ -73,6 +75,14 @@ def _load():
     lib.gpbt_ensemble_end_half.argtypes = [vp, i32, dp, vp]
     lib.gpbt_ensemble_read.argtypes = [vp, i64, i64, dp, dp, dp, dp]
     lib.gpbt_ensemble_reset.argtypes = [vp]
+    lib.gpbt_device_count.argtypes = []
+    lib.gpbt_set_device.argtypes = [i32]
+    lib.gpbt_get_device.argtypes = []
+    lib.gpbt_set_option.argtypes = [C.c_char_p, C.c_char_p]
+    lib.gpbt_fanout_create.argtypes = [C.POINTER(vp), C.POINTER(vp), i32]
+    lib.gpbt_fanout_destroy.argtypes = [vp]
+    lib.gpbt_fanout_size.argtypes = [vp]
+    lib.gpbt_fanout_log_posterior_host.argtypes = [vp, dp, dbl, dp, C.POINTER(i32), i64, i32, i32, C.POINTER(i32)]
     return lib
 
 
@@ -82,6 +92,29 @@ lib = _load()
 def check(rc):
     if rc != 0:
         raise GpbtError("gpbt error %d: %s" % (rc, lib.gpbt_last_error().decode()))
+
+
+def set_option(key, value=None):
+    """gpbt_set_option: tuning override ("pc_tile", "chol", "lowrank_generic", "no_zerocopy",
+    "ensemble_split_kernels", "fanout_min_rows", "chol_batch"); None restores the default."""
+    check(lib.gpbt_set_option(key.encode(), None if value is None else str(value).encode()))
+
+
+class on_device:
+    """`with on_device(i):` makes CUDA device i current for the enclosed C-ABI calls"""
+
+    def __init__(self, device):
+        self.device = device
+
+    def __enter__(self):
+        self.prev = lib.gpbt_get_device()
+        if self.device is not None and self.device != self.prev:
+            check(lib.gpbt_set_device(int(self.device)))
+        return self
+
+    def __exit__(self, *exc):
+        if self.device is not None and self.device != self.prev:
+            lib.gpbt_set_device(self.prev)
 
 
 def host_ptr(a):

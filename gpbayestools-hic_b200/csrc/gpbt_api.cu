@@ -77,17 +77,84 @@ int current_device() {
   return dev;
 }
 
-int max_optin_smem() {
-  static int cache[kMaxDevices] = {0};
+// Properties of a device the launch configuration depends on, queried once per device.
+struct DeviceInfo {
+  int sm_count = 0;        // multiprocessors
+  int smem_optin = 0;      // largest dynamic shared memory a block may opt in to
+  int smem_per_sm = 0;     // shared memory of one multiprocessor (all resident blocks together)
+  int l2_bytes = 0;
+  bool ready = false;
+};
+
+const DeviceInfo& device_info() {
+  static DeviceInfo table[kMaxDevices];
+  static DeviceInfo overflow;
+  static std::mutex mtx;
   const int dev = current_device();
-  if (dev < 0 || dev >= kMaxDevices) {
-    int v = 0;
-    cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    return v;
+  DeviceInfo& d = (dev >= 0 && dev < kMaxDevices) ? table[dev] : overflow;
+  if (!d.ready || &d == &overflow) {
+    std::lock_guard<std::mutex> lock(mtx);
+    cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaDeviceGetAttribute(&d.smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    cudaDeviceGetAttribute(&d.l2_bytes, cudaDevAttrL2CacheSize, dev);
+    d.ready = true;
   }
-  if (cache[dev] == 0) cudaDeviceGetAttribute(&cache[dev], cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  return cache[dev];
+  return d;
 }
+
+int max_optin_smem() { return device_info().smem_optin; }
+
+// Tuning overrides.  The environment (GPBT_PC_TILE, GPBT_CHOL, GPBT_LOWRANK_GENERIC, GPBT_NO_ZEROCOPY,
+// GPBT_ENSEMBLE_SPLIT_KERNELS, GPBT_FANOUT_MIN_ROWS, GPBT_CHOL_BATCH) is read ONCE, when the library is
+// loaded; afterwards gpbt_set_option changes a value (tests, tuning tools).  Nothing on a call path
+// touches getenv.
+struct Options {
+  std::atomic<int> pc_tile{0};              // 0 = automatic, else 8 | 16 | 32
+  std::atomic<int> chol{0};                 // 0 = automatic, else 'w'arp | 'b'atch (stepped) | 's'taged | 'c'ta | 'f'used
+  std::atomic<int> lowrank_generic{0};
+  std::atomic<int> no_zerocopy{0};
+  std::atomic<int> ensemble_split_kernels{0};
+  std::atomic<int64_t> fanout_min_rows{0};  // 0 = built-in default
+  std::atomic<int64_t> chol_batch{0};       // walkers per sub-batch of the fused Cholesky, 0 = automatic
+};
+Options g_opt;
+
+int set_option_value(const char* key, const char* value) {
+  const std::string k = key ? key : "";
+  const char* v = (value && value[0]) ? value : nullptr;
+  if (k == "pc_tile") {
+    const int t = v ? atoi(v) : 0;
+    if (t != 0 && t != 8 && t != 16 && t != 32) return GPBT_EINVAL;
+    g_opt.pc_tile = t;
+  } else if (k == "chol") {
+    g_opt.chol = v ? (int)v[0] : 0;
+  } else if (k == "lowrank_generic") {
+    g_opt.lowrank_generic = v ? atoi(v) : 0;
+  } else if (k == "no_zerocopy") {
+    g_opt.no_zerocopy = v ? atoi(v) : 0;
+  } else if (k == "ensemble_split_kernels") {
+    g_opt.ensemble_split_kernels = v ? atoi(v) : 0;
+  } else if (k == "fanout_min_rows") {
+    g_opt.fanout_min_rows = v ? atoll(v) : 0;
+  } else if (k == "chol_batch") {
+    g_opt.chol_batch = v ? atoll(v) : 0;
+  } else {
+    return GPBT_EINVAL;
+  }
+  return 0;
+}
+
+struct OptionsFromEnvironment {
+  OptionsFromEnvironment() {
+    static const char* const names[][2] = {
+        {"GPBT_PC_TILE", "pc_tile"}, {"GPBT_CHOL", "chol"}, {"GPBT_LOWRANK_GENERIC", "lowrank_generic"},
+        {"GPBT_NO_ZEROCOPY", "no_zerocopy"}, {"GPBT_ENSEMBLE_SPLIT_KERNELS", "ensemble_split_kernels"},
+        {"GPBT_FANOUT_MIN_ROWS", "fanout_min_rows"}, {"GPBT_CHOL_BATCH", "chol_batch"}};
+    for (const auto& n : names)
+      if (const char* e = getenv(n[0])) set_option_value(n[1], e);
+  }
+} g_options_from_environment;
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device setting: remember the largest size
 // configured for each kernel on each device (the kernel is a template argument, so every kernel --
@@ -385,8 +452,9 @@ int launch_pc_predict_p(const PcPredictParams& prm, cudaStream_t st) {
 // GPBT_PC_TILE=8|16|32 overrides (tuning / tests).
 template <int KIND>
 int dispatch_pc_predict(const PcPredictParams& prm, cudaStream_t st) {
-  const size_t limit = (size_t)max_optin_smem();
-  const size_t per_sm = 228 * 1024 - 2048;
+  const DeviceInfo& di = device_info();
+  const size_t limit = (size_t)di.smem_optin;
+  const size_t per_sm = (size_t)di.smem_per_sm - 2048;
   int tw = 16;
   if (2 * (pc_predict_smem_bytes<16>(prm.n_pad, prm.p_pad) + 1024) > per_sm &&
       pc_predict_smem_bytes<32>(prm.n_pad, prm.p_pad) <= limit)
@@ -394,12 +462,9 @@ int dispatch_pc_predict(const PcPredictParams& prm, cudaStream_t st) {
   if (tw == 16 && pc_predict_smem_bytes<16>(prm.n_pad, prm.p_pad) > limit) tw = 8;
   if (tw == 8 && pc_predict_smem_bytes<8>(prm.n_pad, prm.p_pad) > limit)
     return fail(GPBT_ESHAPE, "pc_predict: n = %d design points do not fit in shared memory", prm.n);
-  const int64_t want = 2 * 148;
+  const int64_t want = 2 * di.sm_count;
   while (tw > 8 && ((prm.N + tw - 1) / tw) * prm.q < want) tw >>= 1;
-  if (const char* env = getenv("GPBT_PC_TILE")) {
-    const int v = atoi(env);
-    if (v == 8 || v == 16 || v == 32) tw = v;
-  }
+  if (const int v = g_opt.pc_tile.load()) tw = v;
   if (tw == 32) return launch_pc_predict_p<32, KIND>(prm, st);
   if (tw == 16) return launch_pc_predict_p<16, KIND>(prm, st);
   return launch_pc_predict<8, KIND, 0>(prm, st);
@@ -456,9 +521,10 @@ int run_backtransform(gpbt_emulator_t e, const double* zm, const double* zv, int
       return fail(GPBT_ESHAPE, "backtransform: q*m = %d*%d does not fit in shared memory", e->q, e->m);
     if (int r = ensure_dynamic_smem<backtransform_cov_kernel>(smem)) return r;
     const int64_t items = ((N + kBtGroup - 1) / kBtGroup) * bt_items_per_walker(e->m);   // one per warp
-    int per_sm = (int)std::min<size_t>(4, (228 * 1024 - 4096) / (smem + 1024));
+    const DeviceInfo& di = device_info();
+    int per_sm = (int)std::min<size_t>(4, ((size_t)di.smem_per_sm - 4096) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
-    const unsigned grid = (unsigned)std::min<int64_t>((items + kBtWarps - 1) / kBtWarps, (int64_t)148 * per_sm);
+    const unsigned grid = (unsigned)std::min<int64_t>((items + kBtWarps - 1) / kBtWarps, (int64_t)di.sm_count * per_sm);
     backtransform_cov_kernel<<<grid, kBtThreads, smem, st>>>(prm, e->q_pad);
     LAUNCH_CHECK();
   }
@@ -548,11 +614,11 @@ int run_chol(const double* mean, const double* y_exp, double* cov, const double*
   // Small matrices: warp-per-walker kernel, nine walkers resident per SM (their matrices stay in
   // L2: 1332 x 8m^2 bytes <= ~64 MB).  Larger ones: panel-synchronous kernels over the whole batch,
   // or CTA-per-walker for small batches.  GPBT_CHOL=warp|batch|staged|cta overrides.
-  const char* which = getenv("GPBT_CHOL");
+  const int which = g_opt.chol.load();
   const size_t wsmem = chol_warp_smem_bytes(m);
   bool use_warp = m <= 80;
-  if (which && which[0] == 'w') use_warp = true;
-  if (which && (which[0] == 'c' || which[0] == 's')) use_warp = false;
+  if (which == 'w') use_warp = true;
+  if (which == 'c' || which == 's' || which == 'b') use_warp = false;
   if (use_warp && wsmem <= (size_t)max_optin_smem()) {
     if (int r = ensure_dynamic_smem<chol_warp_kernel>(wsmem)) return r;
     chol_warp_kernel<<<(unsigned)N, 32, wsmem, st>>>(prm);
@@ -564,14 +630,14 @@ int run_chol(const double* mean, const double* y_exp, double* cov, const double*
   // m = 300: 0.92 vs 0.96 ms at N = 512, 9.4 vs 11.2 ms at N = 8192); below that its 19 dependent
   // launches cost more than one latency-bound kernel.  GPBT_CHOL=batch / staged / cta force a variant.
   const bool aligned_rows = (m % 2 == 0) && ((reinterpret_cast<uintptr_t>(cov) & 15) == 0);
-  const bool want_stepped = which ? which[0] == 'b' : N >= 256;
+  const bool want_stepped = which ? which == 'b' : N >= 256;
   if (aligned_rows && want_stepped) return run_chol_stepped(prm, st);
   // staged kernel (operand stream through a cp.async ring): needs 16-byte aligned rows and its
   // fixed block assignment covers m <= 352
   const size_t ssmem = chol_staged_smem_bytes(m);
   const bool can_stage = (m % 2 == 0) && m <= kCsMaxM && ((reinterpret_cast<uintptr_t>(cov) & 15) == 0) &&
                          ssmem <= (size_t)max_optin_smem();
-  if (can_stage && !(which && which[0] == 'c')) {
+  if (can_stage && which != 'c') {
     if (int r = ensure_dynamic_smem<chol_staged_kernel>(ssmem)) return r;
     chol_staged_kernel<<<(unsigned)N, kChThreads, ssmem, st>>>(prm);
     LAUNCH_CHECK();
@@ -1025,7 +1091,7 @@ int log_posterior_impl(gpbt_chain_t ch, const double* X, double oob_value, doubl
       prm.n_peers = n_peers; prm.peer_off = peer_off;
       for (int r = 0; r < n_peers; r++) prm.peers[r] = peers[r];
       const unsigned grid = (unsigned)((N + kLrWarps - 1) / kLrWarps);
-      if (qb <= 32 && !getenv("GPBT_LOWRANK_GENERIC")) {
+      if (qb <= 32 && !g_opt.lowrank_generic.load()) {
         switch ((qb + 3) / 4) {
 #define GPBT_Q(QP) \
   case QP / 4: CU(launch_pdl(lowrank_loglike_reg_kernel<QP>, dim3(grid), kLrWarps * 32, 0, st, prm)); break;
@@ -1104,7 +1170,7 @@ extern "C" int gpbt_log_posterior_host(gpbt_chain_t ch, const double* X_host, do
   if (N == 0) return 0;
   CU(cudaSetDevice(ch->device));
   cudaStream_t st = ch->stream;
-  if (N <= kZeroCopyRows && !getenv("GPBT_NO_ZEROCOPY")) {
+  if (N <= kZeroCopyRows && !g_opt.no_zerocopy.load()) {
     if (!ch->zc_x_host) {
       CU(cudaHostAlloc(&ch->zc_x_host, (size_t)kZeroCopyRows * ch->p * sizeof(double), cudaHostAllocMapped));
       CU(cudaHostAlloc(&ch->zc_lp_host, (size_t)(kZeroCopyRows + 1) * sizeof(double), cudaHostAllocMapped));
@@ -1176,7 +1242,7 @@ int ensemble_enqueue_step(gpbt_ensemble* en, cudaStream_t st) {
   const int nw = en->nw, p = en->p;
   const EnsembleBuffers b = ensemble_buffers(en);
   const size_t key_bytes = (size_t)nw * sizeof(unsigned long long);
-  if (nw <= kEnsembleFusedMaxWalkers && !getenv("GPBT_ENSEMBLE_SPLIT_KERNELS")) {
+  if (nw <= kEnsembleFusedMaxWalkers && !g_opt.ensemble_split_kernels.load()) {
     // small ensemble: launch latency is the cost, three single-CTA kernels around the two calls
     CU(launch_pdl(ensemble_begin_kernel, dim3(1), 1024, key_bytes, st, b));
     LAUNCH_CHECK();
@@ -1207,7 +1273,7 @@ int ensemble_enqueue_step(gpbt_ensemble* en, cudaStream_t st) {
     ensemble_accept_kernel<<<grid, 128, 0, st>>>(b, half);
     LAUNCH_CHECK();
   }
-  const unsigned rec_grid = (unsigned)std::min<int64_t>(((int64_t)nw * p + 255) / 256, 148);
+  const unsigned rec_grid = (unsigned)std::min<int64_t>(((int64_t)nw * p + 255) / 256, device_info().sm_count);
   ensemble_record_kernel<<<rec_grid, 256, 0, st>>>(en->ctl, nw, p, en->x, en->lp, en->rec_done);
   LAUNCH_CHECK();
   return 0;
@@ -1392,7 +1458,7 @@ extern "C" int gpbt_ensemble_end_half(gpbt_ensemble_t en, int half, const double
     LAUNCH_CHECK();
   }
   if (half == 1) {
-    const unsigned rec_grid = (unsigned)std::min<int64_t>(((int64_t)nw * p + 255) / 256, 148);
+    const unsigned rec_grid = (unsigned)std::min<int64_t>(((int64_t)nw * p + 255) / 256, device_info().sm_count);
     ensemble_record_kernel<<<rec_grid, 256, 0, st>>>(en->ctl, nw, p, en->x, en->lp, en->rec_done);
     LAUNCH_CHECK();
     en->steps += 1;
@@ -1513,3 +1579,5 @@ extern "C" int gpbt_host_temp_exchange(const double* lp, const double* temps, in
   }
   return 0;
 }
+
+#include "fanout.inl"

@@ -13,6 +13,12 @@ from . import _lib
 from .state import EmulatorState
 
 _COV_CHUNK_BYTES = 4 << 30  # device bytes of covariance produced per chunk by predict()
+_FANOUT_MIN_ROWS = 1024     # rows per GPU below which a further GPU does not pay (gpbt_fanout_*'s default)
+
+
+def _require_gpu():
+    if _lib.lib.gpbt_device_count() < 1:
+        raise RuntimeError("gpbt_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
 
 
 def _torch():
@@ -149,11 +155,36 @@ def mvn_loglike_batch(dY, cov, notpd_value=-np.inf, cov_add=None):
     return out
 
 
+def default_devices():
+    """CUDA devices a single-process Chain fans large host batches out over.
+    GPBT_DEVICES = "all" | "1" (the current device only) | "0,2,3" (explicit list, first = primary).
+    Default: every visible device -- unless this process is one rank of a multi-process job
+    (WORLD_SIZE > 1, torchrun), where each rank keeps to its own GPU."""
+    import os
+    cur = _lib.lib.gpbt_get_device()
+    spec = os.environ.get("GPBT_DEVICES", "").strip().lower()
+    if spec in ("1", "one", "current") or int(os.environ.get("WORLD_SIZE", "1") or 1) > 1:
+        return [cur]
+    n = _lib.lib.gpbt_device_count()
+    if spec and spec != "all":
+        devs = [int(t) for t in spec.split(",") if t.strip() != ""]
+        bad = [d for d in devs if d < 0 or d >= n]
+        if bad or not devs:
+            raise ValueError("GPBT_DEVICES=%r names devices outside 0..%d" % (spec, n - 1))
+        return devs
+    return [cur] + [d for d in range(n) if d != cur]
+
+
 class DeviceChain:
     """Everything between X[N, p] and lp[N] for a list of emulators + experimental data
-    (gpbt_chain_t).  Builds the low-rank factors on the host when every emulator is PCA-mode."""
+    (gpbt_chain_t).  Builds the low-rank factors on the host when every emulator is PCA-mode.
 
-    def __init__(self, states, lo, hi, y_exp, cov_exp, lowrank=True):
+    device   CUDA device of this chain (default: the one current at first use).
+    devices  devices the HOST call (log_target) may fan a large batch out over, this chain's own device
+             first; replicas on the others are created the first time a batch is large enough
+             (gpbt_fanout_*: one worker thread and one pinned staging buffer per GPU, no collective)."""
+
+    def __init__(self, states, lo, hi, y_exp, cov_exp, lowrank=True, device=None, devices=None):
         self.states = list(states)
         self.p = self.states[0].p_in   # columns of X (before any parameter-function pre-transform)
         self.M = sum(s.m for s in self.states)
@@ -162,26 +193,69 @@ class DeviceChain:
         self.hi = np.ascontiguousarray(hi, dtype=np.float64).reshape(self.p)
         self.y_exp = np.ascontiguousarray(y_exp, dtype=np.float64).reshape(self.M)
         self.cov_exp = np.ascontiguousarray(cov_exp, dtype=np.float64).reshape(self.M, self.M)
+        self.device = device
+        self.devices = None if devices is None else list(devices)
+        if self.devices:
+            if device is not None and self.devices[0] != device:
+                raise ValueError("devices[0] must be the chain's own device")
+            self.device = self.devices[0]
         self.lowrank = None
-        if lowrank and all(not (s.no_pca or s.exp_diag) for s in self.states) and self.Q <= self.M:
-            self.lowrank = lowrank_factors(self.states, self.y_exp, self.cov_exp)
+        self.lowrank_error = None
+        if lowrank is not False and lowrank is not None and not isinstance(lowrank, bool):
+            self.lowrank = lowrank          # factors handed over by the chain this one replicates
+        elif lowrank and all(not (s.no_pca or s.exp_diag) for s in self.states) and self.Q <= self.M:
+            # F = blockdiag(Ctrunc) + cov_exp may be singular although every C_w is positive definite
+            # (zero truncation term of a PCGP emulator + an experimental error of exactly 0): the dense
+            # path handles that case, the factorisation of F cannot
+            try:
+                lr = lowrank_factors(self.states, self.y_exp, self.cov_exp)
+                vals = [lr["s_perp"], lr["logdetF_half"], float(np.abs(lr["R"]).max()), float(np.abs(lr["c0"]).max())]
+                if not np.all(np.isfinite(vals)):
+                    raise np.linalg.LinAlgError("non-finite low-rank factors")
+                self.lowrank = lr
+            except (np.linalg.LinAlgError, ValueError) as exc:
+                import warnings
+                self.lowrank_error = str(exc)
+                warnings.warn("gpbt_b200: truncation + experimental covariance cannot be factorised (%s); "
+                              "using the dense path" % exc)
         self._handle = None
         self._checked = self.lowrank is None
         self.lowrank_check = None
         self._dependents = weakref.WeakSet()   # device samplers bound to the handle
+        self._replicas = []                    # DeviceChain per further device (fan-out)
+        self._fanout = None
+        self.last_devices_used = 1
 
     def handle(self):
         if self._handle is None:
+            if self.device is None:
+                self.device = _lib.lib.gpbt_get_device()
             h = C.c_void_p()
-            arr = (C.c_void_p * len(self.states))(*[s.handle() for s in self.states])
             hp = _lib.host_ptr
             lr = self.lowrank
-            _lib.check(_lib.lib.gpbt_chain_create(
-                C.byref(h), arr, len(self.states), self.p, hp(self.lo), hp(self.hi), hp(self.y_exp),
-                hp(self.cov_exp), hp(lr["R"]) if lr else None, hp(lr["c0"]) if lr else None,
-                lr["s_perp"] if lr else 0.0, lr["logdetF_half"] if lr else 0.0))
+            with _lib.on_device(self.device):
+                arr = (C.c_void_p * len(self.states))(*[s.handle(self.device) for s in self.states])
+                _lib.check(_lib.lib.gpbt_chain_create(
+                    C.byref(h), arr, len(self.states), self.p, hp(self.lo), hp(self.hi), hp(self.y_exp),
+                    hp(self.cov_exp), hp(lr["R"]) if lr else None, hp(lr["c0"]) if lr else None,
+                    lr["s_perp"] if lr else 0.0, lr["logdetF_half"] if lr else 0.0))
             self._handle = h
         return self._handle
+
+    def fanout(self):
+        """gpbt_fanout_t over this chain and one replica per further device of `devices`"""
+        if self._fanout is None:
+            own = self.handle()
+            self._replicas = [DeviceChain(self.states, self.lo, self.hi, self.y_exp, self.cov_exp,
+                                          lowrank=self.lowrank if self.lowrank is not None else False, device=d)
+                              for d in self.devices[1:]]
+            for r in self._replicas:
+                r._checked = True
+            handles = [own] + [r.handle() for r in self._replicas]
+            f = C.c_void_p()
+            _lib.check(_lib.lib.gpbt_fanout_create(C.byref(f), (C.c_void_p * len(handles))(*handles), len(handles)))
+            self._fanout = f
+        return self._fanout
 
     def _self_check(self, n_points=16, tol=1e-8):
         """Once per chain: the exact low-rank path against the dense Cholesky path on a few points of
@@ -191,8 +265,8 @@ class DeviceChain:
         self._checked = True
         rng = np.random.default_rng(20261018)
         X = rng.uniform(self.lo, self.hi, (n_points, self.p))
-        a = self._call_host(X, -np.inf, _lib.PATH_LOWRANK)
-        b = self._call_host(X, -np.inf, _lib.PATH_DENSE)
+        a = self._call_host(X, -np.inf, _lib.PATH_LOWRANK, 1)
+        b = self._call_host(X, -np.inf, _lib.PATH_DENSE, 1)
         ok = np.isfinite(a) & np.isfinite(b)
         diff = float(np.max(np.abs(a[ok] - b[ok]))) if ok.any() else 0.0
         self.lowrank_check = dict(points=int(ok.sum()), max_abs_diff=diff, tol=tol)
@@ -203,18 +277,33 @@ class DeviceChain:
             self.release()
             self.lowrank = None
 
-    def _call_host(self, X, oob_value, path):
+    def _call_host(self, X, oob_value, path, max_devices=None):
         lp = np.empty(X.shape[0])
         notpd = C.c_int(0)
-        _lib.check(_lib.lib.gpbt_log_posterior_host(
-            self.handle(), _lib.host_ptr(X), float(oob_value), _lib.host_ptr(lp), C.byref(notpd),
-            X.shape[0], path))
+        N = X.shape[0]
+        if self.devices and len(self.devices) > 1 and max_devices != 1 and (max_devices or N >= 2 * _FANOUT_MIN_ROWS):
+            used = C.c_int(0)
+            _lib.check(_lib.lib.gpbt_fanout_log_posterior_host(
+                self.fanout(), _lib.host_ptr(X), float(oob_value), _lib.host_ptr(lp), C.byref(notpd), N, path,
+                int(max_devices or 0), C.byref(used)))
+            self.last_devices_used = used.value
+        else:
+            with _lib.on_device(self.device):
+                _lib.check(_lib.lib.gpbt_log_posterior_host(
+                    self.handle(), _lib.host_ptr(X), float(oob_value), _lib.host_ptr(lp), C.byref(notpd), N, path))
+            self.last_devices_used = 1
         self.last_notpd = notpd.value
         return lp
 
     def release(self):
         for dep in list(getattr(self, "_dependents", ())):
             dep.close()
+        if getattr(self, "_fanout", None) is not None:
+            _lib.lib.gpbt_fanout_destroy(self._fanout)   # joins the worker threads
+            self._fanout = None
+        for r in getattr(self, "_replicas", ()):
+            r.release()
+        self._replicas = []
         if self._handle is not None:
             _lib.lib.gpbt_chain_destroy(self._handle)
             self._handle = None
@@ -230,13 +319,15 @@ class DeviceChain:
         return {None: _lib.PATH_AUTO, "auto": _lib.PATH_AUTO, "dense": _lib.PATH_DENSE,
                 "lowrank": _lib.PATH_LOWRANK, "diag": _lib.PATH_DIAG}[path]
 
-    def log_target(self, X, oob_value, path=None):
-        """Host buffers in/out through gpbt_log_posterior_host (H2D, kernels, D2H, one sync)."""
-        _torch()
+    def log_target(self, X, oob_value, path=None, max_devices=None):
+        """Host buffers in/out: gpbt_log_posterior_host (H2D, kernels, D2H, one sync) on this chain's GPU,
+        or -- with `devices` and a batch of at least 2 x 1024 rows -- gpbt_fanout_log_posterior_host over
+        several GPUs.  max_devices: None = automatic, 1 = this GPU only, n = use n GPUs whatever N is."""
+        _require_gpu()
         X = as_rows(X, self.p)
         if not self._checked:
             self._self_check()
-        return self._call_host(X, oob_value, self._path(path))
+        return self._call_host(X, oob_value, self._path(path), max_devices)
 
     def log_target_device(self, X_d, oob_value, lp_d=None, path=None):
         """Device tensors in/out on torch's current stream; no synchronisation."""

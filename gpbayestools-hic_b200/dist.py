@@ -43,9 +43,10 @@ class PeerGather:
         self.buf.zero_()
         self.hdl.barrier(channel=0)
 
-    def evaluate(self, chain, X_local, oob_value, path=None):
+    def evaluate(self, chain, X_local, oob_value, path=None, mid_event=None):
         """chain: DeviceChain.  Returns the gathered vector [world * n_local] (a view of this rank's
-        symmetric buffer, valid until the call after next)."""
+        symmetric buffer, valid until the call after next).  mid_event (a torch.cuda.Event) is recorded
+        between the kernels and the device barrier, for callers that time the two apart."""
         n = X_local.shape[0]
         if n > self.rows:
             raise ValueError("PeerGather was sized for %d rows per rank, got %d" % (self.rows, n))
@@ -53,6 +54,8 @@ class PeerGather:
         self.parity ^= 1
         peers = [p + 8 * half for p in self.ptrs]
         chain.log_target_scatter(X_local, oob_value, peers, self.rank * n, path=path)
+        if mid_event is not None:
+            mid_event.record()
         self.hdl.barrier(channel=0)
         return self.buf[half:half + self.world * n]
 

@@ -19,7 +19,7 @@ from pathlib import Path
 import numpy as np
 
 from . import parse_model_parameter_file
-from .device import DeviceChain, as_rows, mvn_loglike_batch
+from .device import DeviceChain, as_rows, default_devices, mvn_loglike_batch
 from .state import EmulatorState
 
 log = logging.getLogger(__name__)
@@ -77,8 +77,13 @@ class Chain:
         self.nobs = self.expdata.shape[1]
         self.emuList = []
         self.chain = False
+        # GPUs large host batches are spread over: None = automatic (gpbt_b200.device.default_devices: all
+        # visible GPUs of a single-process run, the rank's own GPU under torchrun), or a list of indices
+        self.devices = None
         self._dev = None
         self._dev_key = None
+        self._dev_snapshot = None
+        self._dev_calls = 0
 
     # ---- emulators -----------------------------------------------------------------------
     def loadEmulator(self, emulatorPathList):
@@ -109,19 +114,52 @@ class Chain:
                 out.append(st)
         return out
 
-    def device(self) -> DeviceChain:
-        """Device-resident chain; rebuilt when emuList / expdata / bounds objects change."""
-        key = (tuple(id(e) for e in self.emuList), id(self.expdata), id(self.expdata_cov),
-               id(self.min), id(self.max))
+    _COV_SAMPLE = 97          # stride of the sampled elements of expdata_cov in the per-call check
+    _FULL_CHECK_EVERY = 256   # calls between full comparisons of expdata_cov
+
+    def invalidate(self):
+        """Drop the device-resident copy of the chain; the next call re-uploads emulators, bounds and
+        experimental data.  Needed only after edits the automatic check cannot see (see device())."""
+        if self._dev is not None:
+            self._dev.release()
+        self._dev = None
+        self._dev_key = None
+
+    def _state_key(self, full):
+        """What the device copy was built from.  The reference re-reads min / max / expdata /
+        expdata_cov on every call (src/mcmc.py:188-222), so in-place edits must not leave a stale copy
+        on the GPU: the small arrays are compared in full on every call, expdata_cov (nobs^2 values) by
+        its diagonal and a strided sample on every call and in full every _FULL_CHECK_EVERY calls (and
+        whenever `full` is set: large batches, where the comparison costs nothing)."""
+        cov = np.asarray(self.expdata_cov)
+        key = [tuple(id(e) for e in self.emuList), cov.shape,
+               np.asarray(self.min, dtype=np.float64).tobytes(), np.asarray(self.max, dtype=np.float64).tobytes(),
+               np.asarray(self.expdata, dtype=np.float64).tobytes(),
+               np.ascontiguousarray(cov.diagonal()).tobytes(), cov.ravel()[::self._COV_SAMPLE].tobytes(),
+               None if self.devices is None else tuple(self.devices)]
+        snap = self._dev_snapshot
+        if full and snap is not None and cov.shape == snap.shape and not np.array_equal(cov, snap):
+            key.append("expdata_cov changed")
+        return tuple(key)
+
+    def device(self, rows=0) -> DeviceChain:
+        """Device-resident chain; rebuilt when emuList, the bounds, expdata or expdata_cov change --
+        by assignment or in place (content check, see _state_key; `invalidate()` forces it)."""
+        self._dev_calls += 1
+        full = rows >= 1024 or self._dev_calls % self._FULL_CHECK_EVERY == 0
+        key = self._state_key(full)
         if self._dev is None or key != self._dev_key:
             if not self.emuList:
                 raise RuntimeError("no emulator loaded (call loadEmulator first)")
             if self._dev is not None:
                 self._dev.release()
-            self._dev = DeviceChain(self._states(), self.min, self.max, self.expdata[0], self.expdata_cov)
+            devices = self.devices if self.devices is not None else default_devices()
+            self._dev = DeviceChain(self._states(), self.min, self.max, self.expdata[0], self.expdata_cov,
+                                    devices=devices)
             if self._dev.M != self.nobs:
                 raise ValueError("emulators predict %d observables, experiment has %d" % (self._dev.M, self.nobs))
-            self._dev_key = key
+            self._dev_snapshot = np.array(self.expdata_cov, dtype=np.float64, copy=True)
+            self._dev_key = self._state_key(False)
         return self._dev
 
     # ---- hot path ------------------------------------------------------------------------
@@ -143,16 +181,20 @@ class Chain:
         `finite=True` (what pocoMC needs).  `extra_std_prior_scale` is accepted for signature
         compatibility: the reference multiplies its extra_std by 0.0, which leaves the constant
         2*log(1e-16) and nothing that depends on the scale (src/mcmc.py:199-221)."""
-        return self.device().log_target(X, -1e300 if finite else -np.inf)
+        X = as_rows(X, self.ndim)
+        return self.device(X.shape[0]).log_target(X, -1e300 if finite else -np.inf)
 
     def log_posterior(self, X, extra_std_prior_scale=.05):
         """Posterior at each row of X; identical to log_likelihood(finite=False): the reference
-        adds no log-prior inside the box (src/mcmc.py:261-299)."""
-        return self.device().log_target(X, -np.inf)
+        adds no log-prior inside the box (src/mcmc.py:261-299).  Large batches are spread over the GPUs
+        of `self.devices` from this one process (gpbt_fanout_log_posterior_host)."""
+        X = as_rows(X, self.ndim)
+        return self.device(X.shape[0]).log_target(X, -np.inf)
 
     def log_likelihood_point_by_point(self, X, extra_std_prior_scale=0.001):
         """Same values as the reference's N=1 Python loop (src/mcmc.py:225-258), in one batch."""
-        return self.device().log_target(X, -np.inf)
+        X = as_rows(X, self.ndim)
+        return self.device(X.shape[0]).log_target(X, -np.inf)
 
     def _read_in_exp_data_pickle(self, filepath):
         """values [n_entries, nobs] and diag(err^2) [nobs, nobs] of an experiment pickle (src/mcmc.py:302-324)"""
@@ -178,15 +220,16 @@ class Chain:
 
     # ---- sampler drivers (callers of the hot path; third-party samplers imported lazily) ----
     def run_mcmc(self, nsteps=500, nburnsteps=None, nwalkers=None, status=None, nthin=10,
-                 skip_initial_state_check=False, sampler="device", seed=None):
+                 skip_initial_state_check=False, sampler="emcee", seed=None):
         """Affine-invariant ensemble run with the reference's burn-in recipe: half the burn-in from
         random positions, restart from the best distinct points, second half, then production; the
         thinned chain is appended to `mcmc_path` (src/mcmc.py:345-426).
 
-        sampler="device" (default) keeps the walkers on the GPU for the whole run
-        (gpbt_b200.sampler.DeviceEnsembleSampler: stretch move, one CUDA graph per step);
-        sampler="emcee" drives emcee.EnsembleSampler with pool=self as the reference does, one
-        host call per half-ensemble."""
+        sampler="emcee" (default, what the reference does, src/mcmc.py:372-374) drives
+        emcee.EnsembleSampler with pool=self: one host call of log_posterior per half-ensemble;
+        sampler="device" (opt-in) keeps the walkers on the GPU for the whole run
+        (gpbt_b200.sampler.DeviceEnsembleSampler: the same stretch move, one CUDA graph per step,
+        Philox random numbers keyed by `seed` -- statistically, not draw-for-draw, emcee)."""
         if nburnsteps is None or nwalkers is None:
             log.error("must specify nburnsteps and nwalkers to start chain")
             return
@@ -195,12 +238,18 @@ class Chain:
             with open(self.mcmc_path, "rb") as fh:
                 stored = pickle.load(fh)
         world, rank = _dist_world()
+        start = None
         if sampler == "device" and world > 1:
-            # one process per GPU (torchrun): replicated walkers, proposals evaluated in slices.  Every
-            # rank must arrive here with the same NumPy seed (starting positions) and the same `seed`.
+            # one process per GPU (torchrun): replicated walkers, proposals evaluated in slices.  The
+            # replicas must make identical proposals, so rank 0's seed and starting positions are
+            # broadcast -- the ranks' NumPy generators need not agree.
+            import torch.distributed as dist
             from .sampler import ShardedEnsembleSampler
             if seed is None:
                 seed = int(np.random.randint(0, 2 ** 31 - 1))
+            shared = [int(seed), self.random_pos(nwalkers) if "chain" not in stored else None]
+            dist.broadcast_object_list(shared, src=0)
+            seed, start = shared
             ens = ShardedEnsembleSampler(nwalkers, self.ndim, self.device(), seed=seed)
         elif sampler == "device":
             from .sampler import DeviceEnsembleSampler
@@ -230,7 +279,7 @@ class Chain:
             x0 = stored["chain"][:, -1, :]
         else:
             first = nburnsteps // 2
-            advance(self.random_pos(nwalkers), first)
+            advance(self.random_pos(nwalkers) if start is None else start, first)
             best = np.unique(ens.get_log_prob(flat=True), return_index=True)[1][-nwalkers:]
             x0 = ens.get_chain(flat=True)[best]
             ens.reset()

@@ -39,6 +39,12 @@ class DeviceEnsembleSampler:
             raise ValueError("ndim = %d, but the chain has %d parameters" % (ndim, device_chain.p))
         if nwalkers < 2:
             raise ValueError("need at least 2 walkers")
+        if nwalkers < 2 * ndim:
+            # emcee raises here unless live_dangerously is set; an ensemble of fewer than 2 * ndim walkers
+            # samples only the subspace it spans.  Odd ensemble sizes are a deliberate extension (the two
+            # sets then differ by one walker).
+            log.warning("nwalkers = %d < 2 * ndim = %d: the stretch move cannot leave the subspace the walkers span",
+                        nwalkers, 2 * ndim)
         self.nwalkers, self.ndim, self.a = int(nwalkers), int(ndim), float(a)
         self.use_graph = bool(use_graph)
         if seed is None:

@@ -140,7 +140,7 @@ class EmulatorState:
     trafo: Optional[ParamTrafo] = None    # parameterTrafoPCA pre-transform (then p counts transformed columns)
     sig2: Optional[np.ndarray] = None     # [q]  PCGP only; there c / sn hold (1-nug)a / (1-nug)b, alpha = pw, Linv = Vh^T
     pcgp: Optional[dict] = None           # PCGP only: hypcov [q,p+1], nug [q], Vh [q,n,n] (oracle comparisons)
-    _handle: Optional[C.c_void_p] = field(default=None, repr=False, compare=False)
+    _handles: dict = field(default_factory=dict, repr=False, compare=False)   # CUDA device index -> gpbt_emulator_t
 
     # ---- shapes ---------------------------------------------------------------------------
     @property
@@ -253,50 +253,62 @@ class EmulatorState:
         return 8 * (self.q * n_pad * n_pad + self.q * n_pad * (self.p + 3) + self.m * self.m + self.q * self.m)
 
     # ---- device ---------------------------------------------------------------------------
-    def handle(self):
-        """gpbt_emulator_t for the current CUDA device (created on first use)."""
-        if self._handle is None:
-            from . import _lib
-            h = C.c_void_p()
-            flags = (_lib.FLAG_NO_PCA if self.no_pca else 0) | (_lib.FLAG_EXP_DIAG if self.exp_diag else 0)
-            hp = _lib.host_ptr
-            if self.kind == "PCGP":
-                _lib.check(_lib.lib.gpbt_emulator_create_pcgp(
-                    C.byref(h), self.p, self.n, self.q, self.m, flags, hp(self.Xtr), hp(self.ell), hp(self.c),
-                    hp(self.sn), hp(self.sig2), hp(self.alpha), hp(self.Linv), hp(self.A), hp(self.mu),
-                    hp(self.Ctrunc)))
-            else:
-                kind = {"RBF": _lib.KERNEL_RBF, "Matern": _lib.KERNEL_MATERN32}[self.kind]
-                _lib.check(_lib.lib.gpbt_emulator_create(
-                    C.byref(h), self.p, self.n, self.q, self.m, kind, flags, hp(self.Xtr), hp(self.ell),
-                    hp(self.c), hp(self.sn), hp(self.alpha), hp(self.Linv), hp(self.A), hp(self.mu),
-                    hp(self.scale), hp(self.Ctrunc)))
-            if self.trafo is not None:
-                t = self.trafo
-                ng = len(t.groups)
-                keep = t.keep
-                kinds = np.array([g["kind"] for g in t.groups], dtype=np.int32)
-                idx = np.zeros((ng, 4), dtype=np.int32)
-                for i, g in enumerate(t.groups):
-                    idx[i, :len(g["idx"])] = g["idx"]
-                ncomp = np.array([g["comp"].shape[0] for g in t.groups], dtype=np.int32)
-                npts = np.array([g["grid"][2] for g in t.groups], dtype=np.int32)
-                glo = np.array([g["grid"][0] for g in t.groups], dtype=np.float64)
-                ghi = np.array([g["grid"][1] for g in t.groups], dtype=np.float64)
-                folded = t.folded()
-                Wt = (C.c_void_p * ng)(*[hp(w) for w, _ in folded])
-                bb = (C.c_void_p * ng)(*[hp(b) for _, b in folded])
-                _lib.check(_lib.lib.gpbt_emulator_set_param_trafo(
-                    h, t.p_in, hp(keep), len(keep), ng, hp(kinds), hp(idx), hp(ncomp), hp(npts), hp(glo), hp(ghi),
-                    C.cast(Wt, C.c_void_p), C.cast(bb, C.c_void_p)))
-            self._handle = h
-        return self._handle
+    def handle(self, device=None):
+        """gpbt_emulator_t on CUDA device `device` (default: the current one), created on first use;
+        one replica of the trained state per device."""
+        from . import _lib
+        if device is None:
+            device = _lib.lib.gpbt_get_device()
+        h = self._handles.get(device)
+        if h is None:
+            with _lib.on_device(device):
+                h = self._create_handle(_lib)
+            self._handles[device] = h
+        return h
 
-    def release(self):
-        if self._handle is not None:
-            from . import _lib
-            _lib.lib.gpbt_emulator_destroy(self._handle)
-            self._handle = None
+    def _create_handle(self, _lib):
+        h = C.c_void_p()
+        flags = (_lib.FLAG_NO_PCA if self.no_pca else 0) | (_lib.FLAG_EXP_DIAG if self.exp_diag else 0)
+        hp = _lib.host_ptr
+        if self.kind == "PCGP":
+            _lib.check(_lib.lib.gpbt_emulator_create_pcgp(
+                C.byref(h), self.p, self.n, self.q, self.m, flags, hp(self.Xtr), hp(self.ell), hp(self.c),
+                hp(self.sn), hp(self.sig2), hp(self.alpha), hp(self.Linv), hp(self.A), hp(self.mu),
+                hp(self.Ctrunc)))
+        else:
+            kind = {"RBF": _lib.KERNEL_RBF, "Matern": _lib.KERNEL_MATERN32}[self.kind]
+            _lib.check(_lib.lib.gpbt_emulator_create(
+                C.byref(h), self.p, self.n, self.q, self.m, kind, flags, hp(self.Xtr), hp(self.ell),
+                hp(self.c), hp(self.sn), hp(self.alpha), hp(self.Linv), hp(self.A), hp(self.mu),
+                hp(self.scale), hp(self.Ctrunc)))
+        if self.trafo is not None:
+            t = self.trafo
+            ng = len(t.groups)
+            keep = t.keep
+            kinds = np.array([g["kind"] for g in t.groups], dtype=np.int32)
+            idx = np.zeros((ng, 4), dtype=np.int32)
+            for i, g in enumerate(t.groups):
+                idx[i, :len(g["idx"])] = g["idx"]
+            ncomp = np.array([g["comp"].shape[0] for g in t.groups], dtype=np.int32)
+            npts = np.array([g["grid"][2] for g in t.groups], dtype=np.int32)
+            glo = np.array([g["grid"][0] for g in t.groups], dtype=np.float64)
+            ghi = np.array([g["grid"][1] for g in t.groups], dtype=np.float64)
+            folded = t.folded()
+            Wt = (C.c_void_p * ng)(*[hp(w) for w, _ in folded])
+            bb = (C.c_void_p * ng)(*[hp(b) for _, b in folded])
+            _lib.check(_lib.lib.gpbt_emulator_set_param_trafo(
+                h, t.p_in, hp(keep), len(keep), ng, hp(kinds), hp(idx), hp(ncomp), hp(npts), hp(glo), hp(ghi),
+                C.cast(Wt, C.c_void_p), C.cast(bb, C.c_void_p)))
+        return h
+
+    def release(self, device=None):
+        """destroy the device replicas (all of them, or the one on `device`)"""
+        if not self._handles:
+            return
+        from . import _lib
+        for dev in [d for d in list(self._handles) if device is None or d == device]:
+            with _lib.on_device(dev):
+                _lib.lib.gpbt_emulator_destroy(self._handles.pop(dev))
 
     def __del__(self):
         try:
@@ -306,5 +318,12 @@ class EmulatorState:
 
     def __getstate__(self):
         d = dict(self.__dict__)
-        d["_handle"] = None
+        d["_handles"] = {}
+        d.pop("_handle", None)
         return d
+
+    def __setstate__(self, d):
+        d = dict(d)
+        d.pop("_handle", None)     # pickles written before the per-device table existed
+        d["_handles"] = {}
+        self.__dict__.update(d)

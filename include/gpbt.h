@@ -251,6 +251,35 @@ int gpbt_host_temp_exchange(const double* lp_host, const double* temps_host, int
                             const int64_t* picks_host, const double* log_u_host, int64_t n_picks,
                             int64_t* order_host);
 
+/* ---- single-process multi-GPU fan-out of the host boundary call -------------------------------- *
+ * The reference's samplers are single-process and pass ONE host array to Chain.log_posterior /
+ * log_likelihood (src/mcmc.py:188-222, 261-299; pocoMC hands over all active particles, :798-804).
+ * A fan-out owns replicas of one chain on distinct devices (created by the caller with
+ * gpbt_set_device + gpbt_emulator_create + gpbt_chain_create per device) and one host worker thread per
+ * replica.  gpbt_fanout_log_posterior_host splits X_host [N,p] into contiguous row blocks, each worker
+ * stages its block through pinned memory to its GPU, runs gpbt_log_posterior there and copies its lp
+ * block into lp_host; the call returns when all blocks are back.  No collective is involved.
+ * max_devices: 0 = automatic (one device per `fanout_min_rows` rows, default 1024, at most all),
+ * else the number of replicas to use.  *devices_used (may be NULL) reports how many took part.
+ * The chains stay owned by the caller and must outlive the fan-out.                             */
+typedef struct gpbt_fanout* gpbt_fanout_t;
+int gpbt_device_count(void);
+int gpbt_set_device(int device);
+int gpbt_get_device(void);
+int gpbt_fanout_create(gpbt_fanout_t* out, const gpbt_chain_t* chains, int n_chains);
+int gpbt_fanout_destroy(gpbt_fanout_t fanout);
+int gpbt_fanout_size(gpbt_fanout_t fanout);
+int gpbt_fanout_log_posterior_host(gpbt_fanout_t fanout, const double* X_host, double oob_value,
+                                   double* lp_host, int* n_notpd_host, int64_t N, int path,
+                                   int max_devices, int* devices_used);
+
+/* Tuning overrides (tests, tuning tools).  The library reads GPBT_PC_TILE, GPBT_CHOL,
+ * GPBT_LOWRANK_GENERIC, GPBT_NO_ZEROCOPY, GPBT_ENSEMBLE_SPLIT_KERNELS, GPBT_FANOUT_MIN_ROWS and
+ * GPBT_CHOL_BATCH from the environment once, at load; this call changes one value afterwards.
+ * keys: "pc_tile" (8|16|32), "chol" (warp|batch|staged|cta|fused), "lowrank_generic", "no_zerocopy",
+ * "ensemble_split_kernels", "fanout_min_rows", "chol_batch"; value NULL or "" restores the default. */
+int gpbt_set_option(const char* key, const char* value);
+
 /* bytes of device workspace the chain currently holds (grows with the largest N seen)        */
 int64_t gpbt_chain_workspace_bytes(gpbt_chain_t chain);
 

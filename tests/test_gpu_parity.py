@@ -221,28 +221,28 @@ def test_invariances():
     dense = ch.log_target(X[:500], -np.inf, path="dense")
     assert np.max(np.abs(dense - lp[:500])) <= ABS_LP
     assert ch.log_target(np.empty((0, len(g["lo"]))), -np.inf).shape == (0,)
-    # every walker-tile width of kernel (a) gives the same numbers (GPBT_PC_TILE is the tuning override)
-    import os
+    # every walker-tile width of kernel (a) gives the same numbers ("pc_tile" is the tuning override)
+    from gpbt_b200 import _lib
     try:
         for tile in ("8", "16", "32"):
-            os.environ["GPBT_PC_TILE"] = tile
+            _lib.set_option("pc_tile", tile)
             assert np.max(np.abs(ch.log_target(X[:700], -np.inf) - lp[:700])) <= 1e-10, tile
     finally:
-        os.environ.pop("GPBT_PC_TILE", None)
-    # both Cholesky kernels (warp-per-walker for small m, CTA-per-walker otherwise) agree
+        _lib.set_option("pc_tile", None)
+    # every Cholesky kernel (warp-per-walker, CTA-per-walker, staged, panel-synchronous, fused) agrees
     dense0 = ch.log_target(X[:300], -np.inf, path="dense")
     try:
-        for which in ("warp", "cta", "staged"):
-            os.environ["GPBT_CHOL"] = which
+        for which in ("warp", "cta", "staged", "batch", "fused"):
+            _lib.set_option("chol", which)
             assert np.max(np.abs(ch.log_target(X[:300], -np.inf, path="dense") - dense0)) <= 1e-9, which
     finally:
-        os.environ.pop("GPBT_CHOL", None)
+        _lib.set_option("chol", None)
     # the shared-memory low-rank kernel (fallback for Q > 32) agrees with the register one
     try:
-        os.environ["GPBT_LOWRANK_GENERIC"] = "1"
+        _lib.set_option("lowrank_generic", 1)
         assert np.max(np.abs(ch.log_target(X[:700], -np.inf) - lp[:700])) <= 1e-10
     finally:
-        os.environ.pop("GPBT_LOWRANK_GENERIC", None)
+        _lib.set_option("lowrank_generic", None)
 
 
 def test_exp_accuracy():
@@ -508,16 +508,17 @@ def test_random_shapes_vs_oracle(shape):
     want = orc.log_posterior([ost], X, lo, hi, y_exp.reshape(1, -1), cov_exp)
     fin = np.isfinite(want)
     scale = max(1.0, float(np.max(np.abs(want[fin]), initial=1.0)) / 100.0)
+    from gpbt_b200 import _lib
     try:
         for tile in ("8", "16", "32"):
-            os.environ["GPBT_PC_TILE"] = tile
+            _lib.set_option("pc_tile", tile)
             for path in ("lowrank", "dense"):
                 lp = ch.log_target(X, -np.inf, path=path)
                 assert np.array_equal(np.isneginf(lp), ~fin), (shape, tile, path)
                 if fin.any():
                     assert np.max(np.abs(lp[fin] - want[fin])) <= ABS_LP * scale, (shape, tile, path)
     finally:
-        os.environ.pop("GPBT_PC_TILE", None)
+        _lib.set_option("pc_tile", None)
     if inside.any():
         Xi = X[inside][:9]
         mean, cov = DeviceEmulator(st).predict(Xi, return_cov=True, extra_std=0.03)
@@ -527,7 +528,7 @@ def test_random_shapes_vs_oracle(shape):
 
 
 @pytest.mark.parametrize("m", [96, 130, 300, 602])
-def test_cholesky_variants_agree(m, monkeypatch):
+def test_cholesky_variants_agree(m):
     """gpbt_mvn_loglike through each Cholesky kernel that takes this size (staged default, register-fed
     CTA kernel, warp-per-walker, and the opt-in stepped variant that advances all walkers panel by
     panel) against scipy's dpotrf/dpotrs on random SPD matrices, with and without cov_add, plus a
@@ -543,12 +544,15 @@ def test_cholesky_variants_agree(m, monkeypatch):
     want_add = np.array([orc.mvn_loglike(d, c + add) for d, c in zip(dY, cov)])
     bad = cov.copy()
     bad[5] -= 3.0 * np.eye(m)
-    for which in ("", "cta", "warp", "batch"):
-        if which:
-            monkeypatch.setenv("GPBT_CHOL", which)
-        got = mvn_loglike_batch(dY, cov)
-        assert np.max(np.abs(got - want)) <= ABS_LP, which
-        got = mvn_loglike_batch(dY, cov, cov_add=add)
-        assert np.max(np.abs(got - want_add)) <= ABS_LP, which
-        got = mvn_loglike_batch(dY, bad)
-        assert np.isneginf(got[5]) and np.max(np.abs(np.delete(got, 5) - np.delete(want, 5))) <= ABS_LP, which
+    from gpbt_b200 import _lib
+    try:
+        for which in ("", "cta", "warp", "batch"):
+            _lib.set_option("chol", which or None)
+            got = mvn_loglike_batch(dY, cov)
+            assert np.max(np.abs(got - want)) <= ABS_LP, which
+            got = mvn_loglike_batch(dY, cov, cov_add=add)
+            assert np.max(np.abs(got - want_add)) <= ABS_LP, which
+            got = mvn_loglike_batch(dY, bad)
+            assert np.isneginf(got[5]) and np.max(np.abs(np.delete(got, 5) - np.delete(want, 5))) <= ABS_LP, which
+    finally:
+        _lib.set_option("chol", None)

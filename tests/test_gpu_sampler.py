@@ -157,7 +157,7 @@ def test_run_mcmc_on_device(tmp_path):
     ch = Chain(mcmc_path=str(tmp_path / "mcmc" / "chain.pkl"), expdata_path=paths["exp"], model_parafile=paths["par"])
     ch.emuList = states
     np.random.seed(0)
-    ch.run_mcmc(nsteps=30, nburnsteps=20, nwalkers=16, nthin=3, seed=4)
+    ch.run_mcmc(nsteps=30, nburnsteps=20, nwalkers=16, nthin=3, seed=4, sampler="device")
     with open(ch.mcmc_path, "rb") as fh:
         chain = pickle.load(fh)["chain"]
     assert chain.shape == (16, 10, 5)
@@ -167,7 +167,7 @@ def test_run_mcmc_on_device(tmp_path):
     want = orc.log_posterior(sts, flat[:12], ch.min, ch.max, ch.expdata, ch.expdata_cov)
     assert np.all(np.isfinite(lp)) and np.max(np.abs(lp[:12] - want)) <= ABS_LP
     assert ch.acceptance_fraction_.shape == (16,) and ch.acceptance_fraction_.max() > 0
-    ch.run_mcmc(nsteps=6, nburnsteps=20, nwalkers=16, nthin=3, seed=5)
+    ch.run_mcmc(nsteps=6, nburnsteps=20, nwalkers=16, nthin=3, seed=5, sampler="device")
     with open(ch.mcmc_path, "rb") as fh:
         again = pickle.load(fh)["chain"]
     assert again.shape == (16, 12, 5)
@@ -176,7 +176,7 @@ def test_run_mcmc_on_device(tmp_path):
     ch2 = Chain(mcmc_path=str(tmp_path / "mcmc" / "chain2.pkl"), expdata_path=paths["exp"], model_parafile=paths["par"])
     ch2.emuList = states
     np.random.seed(0)
-    ch2.run_mcmc(nsteps=30, nburnsteps=20, nwalkers=16, nthin=3, seed=4)
+    ch2.run_mcmc(nsteps=30, nburnsteps=20, nwalkers=16, nthin=3, seed=4, sampler="device")
     np.testing.assert_array_equal(ch2.chain, chain)
 
 

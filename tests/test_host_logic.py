@@ -288,3 +288,67 @@ def test_emulator_band_host_side(tmp_path):
     from oracle import gp_oracle as orc
     zm, zv = orc.pc_predict(st.oracle_dict(), info["theta"])
     assert zv.max() < 0.05 * st.sig2.max() and np.all(zv >= 0)
+
+
+def test_singular_truncation_plus_experiment_falls_back_to_dense():
+    """F = blockdiag(Ctrunc) + cov_exp singular (zero truncation term, as on the PCGP path, and an
+    experimental error of exactly 0 -- read_experiment_pickle turns NaN errors into 0): the chain must
+    come up without low-rank factors (dense path), not raise at construction."""
+    import warnings
+    import gpbt_b200  # noqa: F401
+    from types import SimpleNamespace
+    from gpbt_b200.device import DeviceChain
+    rng = np.random.default_rng(3)
+    m, q = 6, 2
+    st = SimpleNamespace(m=m, q=q, p_in=3, A=rng.normal(size=(q, m)), mu=np.zeros(m), Ctrunc=np.zeros((m, m)),
+                         no_pca=False, exp_diag=False)
+    cov_exp = np.diag([0.1, 0.2, 0.0, 0.3, 0.1, 0.2])
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        dc = DeviceChain([st], np.zeros(3), np.ones(3), np.zeros(m), cov_exp)
+    assert dc.lowrank is None and dc.lowrank_error and dc._checked
+    assert any("dense path" in str(x.message) for x in w)
+
+
+def test_default_devices_policy(monkeypatch):
+    """single process: all visible devices, current first; one rank of a torchrun job: its own only;
+    GPBT_DEVICES narrows or pins the list"""
+    import gpbt_b200  # noqa: F401
+    from gpbt_b200 import _lib, device
+    n = _lib.lib.gpbt_device_count()
+    monkeypatch.delenv("GPBT_DEVICES", raising=False)
+    monkeypatch.setenv("WORLD_SIZE", "4")
+    assert len(device.default_devices()) == 1
+    monkeypatch.setenv("WORLD_SIZE", "1")
+    monkeypatch.setenv("GPBT_DEVICES", "1")
+    assert len(device.default_devices()) == 1
+    monkeypatch.delenv("GPBT_DEVICES")
+    assert len(device.default_devices()) == max(n, 1)
+    monkeypatch.setenv("GPBT_DEVICES", "7,9")
+    if n < 10:
+        with pytest.raises(ValueError):
+            device.default_devices()
+
+
+def test_chain_state_key_sees_in_place_edits(tmp_path):
+    """Chain.device() must notice in-place edits of the bounds / experimental data (the reference re-reads
+    them on every call): the key is content based."""
+    import pickle
+    import gpbt_b200  # noqa: F401
+    from gpbt_b200.mcmc import Chain
+    syn = goldens.synthetic_module()
+    paths = syn.write_fixture(str(tmp_path), 3, 12, 5)
+    ch = Chain(mcmc_path=str(tmp_path / "mcmc" / "chain.pkl"), expdata_path=paths["exp"], model_parafile=paths["par"])
+    ch.emuList = [object()]
+    k0 = ch._state_key(False)
+    ch.min[1] += 0.25
+    k1 = ch._state_key(False)
+    assert k1 != k0
+    ch.expdata_cov[2, 2] *= 2.0                      # diagonal: seen by the per-call check
+    k2 = ch._state_key(False)
+    assert k2 != k1
+    ch._dev_snapshot = ch.expdata_cov.copy()
+    ch.expdata_cov[3, 1] += 1e-3                     # off the sampled set: seen by the full check
+    assert ch._state_key(True) != ch._state_key(False) or ch._state_key(False) != k2
+    ch.devices = [0]
+    assert ch._state_key(False) != k2

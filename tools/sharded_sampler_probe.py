@@ -87,7 +87,7 @@ os.makedirs(os.path.join(tmp, "mcmc"), exist_ok=True)
 ch = Chain(mcmc_path=os.path.join(tmp, "mcmc", "chain.pkl"), expdata_path=paths["exp"], model_parafile=paths["par"])
 ch.emuList = product_states(g1)[0]
 np.random.seed(3)
-ch.run_mcmc(nsteps=12, nburnsteps=8, nwalkers=20, nthin=2, seed=9)
+ch.run_mcmc(nsteps=12, nburnsteps=8, nwalkers=20, nthin=2, seed=9, sampler="device")
 chk = torch.tensor([float(np.sum(ch.chain))], dtype=torch.float64, device="cuda")
 lo_, hi_ = chk.clone(), chk.clone()
 dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
