@@ -16,6 +16,7 @@
 #include "backtransform.cuh"
 #include "chol_loglike.cuh"
 #include "chol_staged.cuh"
+#include "chol_fused.cuh"
 #include "chol_stepped.cuh"
 #include "chol_warp.cuh"
 #include "common.cuh"
@@ -117,8 +118,13 @@ struct Options {
   std::atomic<int> ensemble_split_kernels{0};
   std::atomic<int64_t> fanout_min_rows{0};  // 0 = built-in default
   std::atomic<int64_t> chol_batch{0};       // walkers per sub-batch of the fused Cholesky, 0 = automatic
+  std::atomic<int64_t> chol_streams{0};     // streams the fused Cholesky spreads its sub-batches over, 0 = automatic
+  std::atomic<int> cf_debug{0};             // record clock64 stamps of the fused Cholesky (tuning tool)
 };
 Options g_opt;
+long long* g_cf_dbg = nullptr;            // managed buffer of the fused Cholesky's timing stamps (option cf_debug)
+constexpr size_t kCfDbgBytes = 16 * 32 * 8 * 8 * sizeof(long long);
+constexpr int kCfMaxStreams = 4;
 
 int set_option_value(const char* key, const char* value) {
   const std::string k = key ? key : "";
@@ -139,6 +145,10 @@ int set_option_value(const char* key, const char* value) {
     g_opt.fanout_min_rows = v ? atoll(v) : 0;
   } else if (k == "chol_batch") {
     g_opt.chol_batch = v ? atoll(v) : 0;
+  } else if (k == "chol_streams") {
+    g_opt.chol_streams = v ? atoll(v) : 0;
+  } else if (k == "cf_debug") {
+    g_opt.cf_debug = v ? atoi(v) : 0;
   } else {
     return GPBT_EINVAL;
   }
@@ -150,7 +160,8 @@ struct OptionsFromEnvironment {
     static const char* const names[][2] = {
         {"GPBT_PC_TILE", "pc_tile"}, {"GPBT_CHOL", "chol"}, {"GPBT_LOWRANK_GENERIC", "lowrank_generic"},
         {"GPBT_NO_ZEROCOPY", "no_zerocopy"}, {"GPBT_ENSEMBLE_SPLIT_KERNELS", "ensemble_split_kernels"},
-        {"GPBT_FANOUT_MIN_ROWS", "fanout_min_rows"}, {"GPBT_CHOL_BATCH", "chol_batch"}};
+        {"GPBT_FANOUT_MIN_ROWS", "fanout_min_rows"}, {"GPBT_CHOL_BATCH", "chol_batch"},
+        {"GPBT_CHOL_STREAMS", "chol_streams"}};
     for (const auto& n : names)
       if (const char* e = getenv(n[0])) set_option_value(n[1], e);
   }
@@ -217,6 +228,16 @@ struct gpbt_chain {
   // covariances and needs no cov_add pass
   bool exp_blockdiag = false;
   std::vector<double*> base_like;
+  // fused (b)+(c) dense path (chol_fused.cuh): F = blockdiag(Ctrunc) + cov_exp in the factor's packed
+  // panel layout, its diagonal blocks, U^T; per-walker factor / work vectors grown on demand
+  bool has_fused = false;
+  int Mg = 0, Qp = 0;
+  int64_t Lstride = 0, cap_fused = 0;
+  double *cf_Fp = nullptr, *cf_Fd = nullptr, *cf_UT = nullptr;
+  double *cf_L = nullptr, *cf_dinv = nullptr, *cf_draw = nullptr, *cf_tvec = nullptr, *cf_logdet = nullptr, *cf_tsq = nullptr, *cf_mean = nullptr;
+  int* cf_bad = nullptr;
+  cudaStream_t cf_streams[4] = {nullptr, nullptr, nullptr, nullptr};   // [0] unused: the caller's stream
+  cudaEvent_t cf_done[4] = {nullptr, nullptr, nullptr, nullptr}, cf_fork = nullptr;
   bool lr_separable = false;          // R is block diagonal over the emulators
   std::vector<double*> R_blocks;      // per-emulator q_e x q_e copies of the diagonal blocks of R
   double s_perp, logdetF_half;
@@ -741,6 +762,14 @@ __global__ void debug_exp_neg_kernel(const double* __restrict__ x, double* __res
   if (i < n) y[i] = exp_neg(x[i], tab);
 }
 
+extern "C" int gpbt_debug_timing_read(void* dst_host, int64_t bytes) {
+  if (!dst_host || bytes < 0 || (size_t)bytes > kCfDbgBytes) return fail(GPBT_EINVAL, "gpbt_debug_timing_read: bad argument");
+  if (!g_cf_dbg) return fail(GPBT_EINVAL, "gpbt_debug_timing_read: nothing recorded (option cf_debug)");
+  CU(cudaDeviceSynchronize());
+  memcpy(dst_host, g_cf_dbg, (size_t)bytes);
+  return 0;
+}
+
 extern "C" int gpbt_debug_exp_neg(const double* x, double* y, int64_t n, void* stream) {
   if (!x || !y || n < 0) return fail(GPBT_EINVAL, "gpbt_debug_exp_neg: bad argument");
   if (n == 0) return 0;
@@ -871,6 +900,45 @@ int chain_build(gpbt_chain* ch, const gpbt_emulator_t* emus, int n_emu, int p, c
       }
     }
   }
+  if (all_pca) {
+    // constants of the fused dense path: F and U on the host, then packed
+    const int M = ch->M, Q = ch->Q;
+    ch->Mg = (int)round_up(M, 16);
+    ch->Qp = (int)round_up(Q, 4);
+    ch->Lstride = cf_factor_doubles(M);
+    const int Mg = ch->Mg, Qp = ch->Qp, nP = (Mg + kCfNB - 1) / kCfNB;
+    std::vector<double> F(cov_exp, cov_exp + (size_t)M * M), UT((size_t)Mg * Qp, 0.0);
+    for (int e = 0; e < n_emu; e++) {
+      const int m0 = ch->m_off[e], q0 = ch->q_off[e], me = emus[e]->m, qe = emus[e]->q, mld = emus[e]->m_ld;
+      std::vector<double> ct((size_t)me * me), a((size_t)emus[e]->q_pad * mld);
+      CU(cudaMemcpy(ct.data(), emus[e]->Ctrunc, ct.size() * sizeof(double), cudaMemcpyDeviceToHost));
+      CU(cudaMemcpy(a.data(), emus[e]->A, a.size() * sizeof(double), cudaMemcpyDeviceToHost));
+      for (int r = 0; r < me; r++)
+        for (int c2 = 0; c2 < me; c2++) F[(size_t)(m0 + r) * M + m0 + c2] += ct[(size_t)r * me + c2];
+      for (int k = 0; k < qe; k++)
+        for (int o = 0; o < me; o++) UT[(size_t)(m0 + o) * Qp + q0 + k] = a[(size_t)k * mld + o];
+    }
+    std::vector<double> Fp((size_t)std::max<int64_t>(ch->Lstride, 1), 0.0), Fd((size_t)nP * kCfNB * kCfNB, 0.0);
+    for (int K = 0; K < nP; K++) {
+      for (int r = 0; r < kCfNB; r++)
+        for (int c2 = 0; c2 < kCfNB; c2++) {
+          const int gr = kCfNB * K + r, gc = kCfNB * K + c2;
+          Fd[((size_t)K * kCfNB + r) * kCfNB + c2] = (gr < M && gc < M) ? F[(size_t)gr * M + gc] : (r == c2 ? 1.0 : 0.0);
+        }
+      const int rows = cf_panel_rows(Mg, K);
+      const int64_t off = cf_panel_off(Mg, K);
+      for (int sub = 0; sub < 4; sub++)
+        for (int rel = 0; rel < rows; rel++)
+          for (int c8 = 0; c8 < 8; c8++) {
+            const int gr = kCfNB * K + kCfNB + rel, gc = kCfNB * K + 8 * sub + c8;
+            if (gr < M && gc < M) Fp[off + ((size_t)sub * rows + rel) * 8 + c8] = F[(size_t)gr * M + gc];
+          }
+    }
+    if (int r = upload(&ch->cf_Fp, Fp)) return r;
+    if (int r = upload(&ch->cf_Fd, Fd)) return r;
+    if (int r = upload(&ch->cf_UT, UT)) return r;
+    ch->has_fused = true;
+  }
   ch->R = nullptr; ch->c0 = nullptr;
   if (R) {
     h.assign(R, R + (size_t)ch->Q * ch->Q); if (int r = upload(&ch->R, h)) return r;
@@ -910,12 +978,18 @@ void release_stepped_buffer(int device, cudaStream_t st);   // defined next to r
 extern "C" int gpbt_chain_destroy(gpbt_chain_t ch) {
   if (!ch) return 0;
   if (ch->stream) release_stepped_buffer(ch->device, ch->stream);
+  for (int i = 0; i < 4; i++) {
+    if (ch->cf_streams[i]) cudaStreamDestroy(ch->cf_streams[i]);
+    if (ch->cf_done[i]) cudaEventDestroy(ch->cf_done[i]);
+  }
+  if (ch->cf_fork) cudaEventDestroy(ch->cf_fork);
   for (double* d : ch->R_blocks) cudaFree(d);
   for (double* d : ch->base_like) cudaFree(d);
   if (ch->zc_x_host) cudaFreeHost(ch->zc_x_host);
   if (ch->zc_lp_host) cudaFreeHost(ch->zc_lp_host);
   void* ptrs[] = {ch->lo, ch->hi, ch->y_exp, ch->cov_exp, ch->R, ch->c0, ch->z_mean, ch->z_var, ch->extra,
-                  ch->mean, ch->cov, ch->x_dev, ch->lp_dev, ch->skip, ch->notpd_dev, ch->dmean, ch->dvar};
+                  ch->mean, ch->cov, ch->x_dev, ch->lp_dev, ch->skip, ch->notpd_dev, ch->dmean, ch->dvar,
+                  ch->cf_Fp, ch->cf_Fd, ch->cf_UT, ch->cf_L, ch->cf_dinv, ch->cf_draw, ch->cf_tvec, ch->cf_logdet, ch->cf_tsq, ch->cf_bad, ch->cf_mean};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   if (ch->stream) cudaStreamDestroy(ch->stream);
@@ -981,6 +1055,104 @@ int ensure_io(gpbt_chain* ch, int64_t N) {
   CU(cudaMalloc(&ch->lp_dev, (size_t)cap * sizeof(double)));
   ch->ws_bytes += cap * ((int64_t)ch->p * 8 + 8);
   ch->cap_x = cap;
+  return 0;
+}
+
+// fused dense path: per-walker factor panels and work vectors, mean [rows, M]
+int64_t fused_bytes_per_row(const gpbt_chain* ch) {
+  return (ch->Lstride + 2 * kCfNB * kCfNB + ch->Mg + 2 + ch->M) * (int64_t)sizeof(double) + (int64_t)sizeof(int);
+}
+
+int64_t fused_chunk_rows(const gpbt_chain* ch, int64_t N) {
+  size_t free_b = 0, total_b = 0;
+  cudaMemGetInfo(&free_b, &total_b);
+  const size_t per_row = (size_t)fused_bytes_per_row(ch);
+  const size_t budget = std::min<size_t>((size_t)24 << 30, free_b / 2 + (size_t)ch->cap_fused * per_row);
+  int64_t rows = (int64_t)std::max<size_t>(budget / per_row, 1);
+  rows = std::min<int64_t>(rows, 65536);
+  return std::min<int64_t>(rows, N);
+}
+
+int ensure_fused(gpbt_chain* ch, int64_t rows) {
+  if (rows <= ch->cap_fused) return 0;
+  void* old[] = {ch->cf_L, ch->cf_dinv, ch->cf_draw, ch->cf_tvec, ch->cf_logdet, ch->cf_tsq, ch->cf_bad, ch->cf_mean};
+  for (void* p : old)
+    if (p) cudaFree(p);
+  ch->cf_L = ch->cf_dinv = ch->cf_draw = ch->cf_tvec = ch->cf_logdet = ch->cf_tsq = ch->cf_mean = nullptr;
+  ch->cf_bad = nullptr;
+  ch->ws_bytes -= ch->cap_fused * fused_bytes_per_row(ch);
+  ch->cap_fused = 0;
+  CU(cudaMalloc(&ch->cf_L, (size_t)rows * std::max<int64_t>(ch->Lstride, 1) * sizeof(double)));
+  CU(cudaMalloc(&ch->cf_dinv, (size_t)rows * kCfNB * kCfNB * sizeof(double)));
+  CU(cudaMalloc(&ch->cf_draw, (size_t)rows * kCfNB * kCfNB * sizeof(double)));
+  CU(cudaMalloc(&ch->cf_tvec, (size_t)rows * ch->Mg * sizeof(double)));
+  CU(cudaMalloc(&ch->cf_logdet, (size_t)rows * sizeof(double)));
+  CU(cudaMalloc(&ch->cf_tsq, (size_t)rows * sizeof(double)));
+  CU(cudaMalloc(&ch->cf_bad, (size_t)rows * sizeof(int)));
+  CU(cudaMalloc(&ch->cf_mean, (size_t)rows * ch->M * sizeof(double)));
+  ch->ws_bytes += rows * fused_bytes_per_row(ch);
+  ch->cap_fused = rows;
+  g_ws_generation++;
+  return 0;
+}
+
+// (b) + (c) fused: lp[w] from z_var (kernel (a)) and mean, for walkers [0, N) of the chunk.  One launch
+// per 32-column panel; the walkers go through in sub-batches whose factors stay L2 resident
+// (option "chol_batch", default: what fits in ~60 % of the L2).
+int run_chol_fused(gpbt_chain* ch, double* lp, int* n_notpd, double notpd_value, int64_t N, cudaStream_t st) {
+  CholFusedParams prm;
+  prm.Fp = ch->cf_Fp; prm.Fd = ch->cf_Fd; prm.UT = ch->cf_UT; prm.z_var = ch->z_var; prm.mean = ch->cf_mean;
+  prm.y_exp = ch->y_exp; prm.skip = ch->skip; prm.L = ch->cf_L; prm.dinv = ch->cf_dinv; prm.draw = ch->cf_draw; prm.tvec = ch->cf_tvec;
+  prm.logdet = ch->cf_logdet; prm.tsq = ch->cf_tsq; prm.bad = ch->cf_bad; prm.lp = lp; prm.n_notpd = n_notpd;
+  prm.notpd_value = notpd_value; prm.add_const = kSysConst; prm.N = N; prm.Lstride = ch->Lstride; prm.ldz = ch->Q;
+  prm.M = ch->M; prm.Mg = ch->Mg; prm.Q = ch->Q; prm.Qp = ch->Qp;
+  prm.dbg = nullptr;
+  if (g_opt.cf_debug.load()) {
+    if (!g_cf_dbg) CU(cudaMallocManaged(&g_cf_dbg, kCfDbgBytes));
+    prm.dbg = g_cf_dbg;
+  }
+  const size_t smem = chol_fused_smem_bytes(ch->Mg);
+  if (smem > (size_t)max_optin_smem()) return fail(GPBT_ESHAPE, "fused Cholesky: M = %d observables do not fit", ch->M);
+  if (int r = ensure_dynamic_smem<chol_fused_panel_kernel>(smem)) return r;
+  if (int r = ensure_dynamic_smem<chol_fused_factor_kernel>(kCfFactorSmem)) return r;
+  // Sub-batches go round-robin over up to kCfMaxStreams streams (the caller's + the chain's own): while one
+  // sub-batch is in its factor kernel or in the tail of a panel launch, the DMMA work of another fills
+  // the machine.  Options "chol_streams" / "chol_batch" override the defaults.
+  int n_streams = (int)g_opt.chol_streams.load();
+  if (n_streams <= 0) n_streams = N >= 2048 ? 2 : 1;
+  n_streams = std::min(n_streams, kCfMaxStreams);
+  int64_t batch = g_opt.chol_batch.load();
+  if (batch <= 0) batch = std::max<int64_t>(512, (N + n_streams - 1) / n_streams);
+  batch = std::min<int64_t>(batch, 32768);          // grid.y carries the walker
+  const int64_t n_batches = (N + batch - 1) / batch;
+  n_streams = (int)std::min<int64_t>(n_streams, n_batches);
+  if (n_streams > 1) {
+    for (int i = 1; i < n_streams; i++)
+      if (!ch->cf_streams[i]) {
+        CU(cudaStreamCreateWithFlags(&ch->cf_streams[i], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&ch->cf_done[i], cudaEventDisableTiming));
+      }
+    if (!ch->cf_fork) CU(cudaEventCreateWithFlags(&ch->cf_fork, cudaEventDisableTiming));
+    CU(cudaEventRecord(ch->cf_fork, st));
+    for (int i = 1; i < n_streams; i++) CU(cudaStreamWaitEvent(ch->cf_streams[i], ch->cf_fork, 0));
+  }
+  const int Mg = ch->Mg;
+  for (int64_t b = 0; b < n_batches; b++) {
+    const int64_t w0 = b * batch, nw = std::min(batch, N - w0);
+    cudaStream_t sb = (b % n_streams == 0) ? st : ch->cf_streams[b % n_streams];
+    for (int J = -kCfNB; J + kCfNB < Mg; J += kCfNB) {
+      const int tiles = (J >= 0 && Mg > J + 2 * kCfNB) ? (Mg - J - 2 * kCfNB + kCfRows - 1) / kCfRows : 0;
+      CU(launch_pdl(chol_fused_panel_kernel, dim3((unsigned)(1 + tiles), (unsigned)nw), kCfThreads, smem, sb, prm, J, w0));
+      LAUNCH_CHECK();
+      CU(launch_pdl(chol_fused_factor_kernel, dim3((unsigned)((nw + kCfFactorWarps - 1) / kCfFactorWarps)),
+                    kCfFactorWarps * 32, kCfFactorSmem, sb, prm, J + kCfNB, w0, nw));
+      LAUNCH_CHECK();
+    }
+  }
+  for (int i = 1; i < n_streams; i++) {
+    CU(cudaEventRecord(ch->cf_done[i], ch->cf_streams[i]));
+    CU(cudaStreamWaitEvent(st, ch->cf_done[i], 0));
+  }
   return 0;
 }
 
@@ -1144,6 +1316,24 @@ int log_posterior_impl(gpbt_chain_t ch, const double* X, double oob_value, doubl
     return scatter_result(lp, peers, n_peers, peer_off, N, st);
   }
 
+  // dense path, PCA-mode chains with more than 80 observables: (a) -> fused (b)+(c), the covariance is
+  // generated tile by tile inside the panel-synchronous Cholesky and never stored (chol_fused.cuh)
+  const int chol_opt = g_opt.chol.load();
+  if (ch->has_fused && (chol_opt == 'f' || (chol_opt == 0 && ch->M > 80 && N >= 64))) {
+    const int64_t chunk = fused_chunk_rows(ch, N);
+    if (int r = ensure_fused(ch, chunk)) return r;
+    if (int r = ensure_rows(ch, chunk)) return r;
+    for (int64_t s = 0; s < N; s += chunk) {
+      const int64_t nn = std::min(chunk, N - s);
+      const double* Xs = X + s * ch->p;
+      bounds_mask_kernel<<<(unsigned)((nn + 127) / 128), 128, 0, st>>>(Xs, ch->lo, ch->hi, ch->p, nn, oob_value,
+                                                                       ch->skip, lp + s);
+      LAUNCH_CHECK();
+      if (int r = chain_predict_rows(ch, Xs, 0.0, ch->cf_mean, nullptr, nn, st)) return r;
+      if (int r = run_chol_fused(ch, lp + s, n_notpd, oob_value, nn, st)) return r;
+    }
+    return scatter_result(lp, peers, n_peers, peer_off, N, st);
+  }
   // dense path: (a) -> (b) with the covariance materialised in HBM -> (c), in row chunks
   const int64_t chunk = dense_chunk_rows(ch, N);
   if (int r = ensure_dense(ch, chunk)) return r;

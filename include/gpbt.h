@@ -277,7 +277,7 @@ int gpbt_fanout_log_posterior_host(gpbt_fanout_t fanout, const double* X_host, d
  * GPBT_LOWRANK_GENERIC, GPBT_NO_ZEROCOPY, GPBT_ENSEMBLE_SPLIT_KERNELS, GPBT_FANOUT_MIN_ROWS and
  * GPBT_CHOL_BATCH from the environment once, at load; this call changes one value afterwards.
  * keys: "pc_tile" (8|16|32), "chol" (warp|batch|staged|cta|fused), "lowrank_generic", "no_zerocopy",
- * "ensemble_split_kernels", "fanout_min_rows", "chol_batch"; value NULL or "" restores the default. */
+ * "ensemble_split_kernels", "fanout_min_rows", "chol_batch", "cf_debug"; value NULL or "" restores the default. */
 int gpbt_set_option(const char* key, const char* value);
 
 /* bytes of device workspace the chain currently holds (grows with the largest N seen)        */
@@ -285,6 +285,10 @@ int64_t gpbt_chain_workspace_bytes(gpbt_chain_t chain);
 
 /* test hook: y[i] = the kernels' internal exp(x[i]) for x <= 0 (accuracy is pinned by a test)  */
 int gpbt_debug_exp_neg(const double* x_dev, double* y_dev, int64_t n, void* stream);
+
+/* tuning hook: with option "cf_debug" the fused Cholesky records clock64 stamps of its phases for the
+ * first 32 walkers, [16 launches][32 walkers][8 tiles][8 stamps] int64; this copies them out        */
+int gpbt_debug_timing_read(void* dst_host, int64_t bytes);
 
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches)      */
 int64_t gpbt_launch_count(void);

@@ -220,7 +220,10 @@ CASES = {
     "p20_trafo": (20, 90, [dict(m=16, q=6, kind="RBF", param_trafo=True)], 64, 9, 8),
 }
 SHIFT = {"p20_trafo": 0.05}
-C2_CASE = {"c2_rbf": (17, 500, [dict(m=300, q=20, kind="RBF")], 1024, 3, 1)}
+C2_CASE = {"c2_rbf": (17, 500, [dict(m=300, q=20, kind="RBF")], 1024, 3, 1),
+           # the config-2 shape trained with the reference's kernel_type="Matern" (kernel (a) kind 1 at n = 500)
+           "c2_matern": (17, 500, [dict(m=300, q=20, kind="Matern")], 256, 4, 1)}
+STORE_L = set()   # cases above n = 100 whose file should carry the reference's L_ (1 MB per PC at n = 500)
 
 
 def main():
@@ -238,7 +241,7 @@ def main():
         if only and name not in only:
             continue
         make_case(name, syn, Emulator, Chain, mvn_loglike, p, n, emus, N, seed, keep,
-                  store_L=(n <= 100), shift=SHIFT.get(name, 0.0))
+                  store_L=(n <= 100 or name in STORE_L), shift=SHIFT.get(name, 0.0))
 
 
 if __name__ == "__main__":

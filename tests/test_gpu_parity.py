@@ -5,10 +5,10 @@ import pytest
 
 from oracle import gp_oracle as orc
 from tests import goldens
-from tests.helpers import ABS_LP, REL, pc_scale, product_states, rel_err, scaled_err
+from tests.helpers import ABS_LP, REL, golden_tol, var_tol, pc_scale, product_states, rel_err, scaled_err
 
 pytestmark = pytest.mark.gpu
-CASES = [c for c in goldens.SMALL_CASES + ["c2_rbf"] if c in goldens.available()]
+CASES = [c for c in goldens.SMALL_CASES + ["c2_rbf", "c2_matern"] if c in goldens.available()]
 
 
 @pytest.fixture(scope="module", params=CASES)
@@ -35,13 +35,13 @@ def test_pc_predict(case):
             continue
         zm, zv = DeviceEmulator(st).pc_predict_device(torch.from_numpy(Xin).cuda())
         zm, zv = zm.cpu().numpy(), zv.cpu().numpy()
-        # variance: 1e-9 relative (it already contains the k** - |L^-1 k|^2 cancellation)
-        assert rel_err(zv, g["e%d_z_var" % e]) <= REL, name
+        # variance: 1e-9 relative + 64 ulp of the terms that cancel in k** - |L^-1 k|^2 (tests/helpers.py)
+        assert np.all(np.abs(zv - g["e%d_z_var" % e]) <= var_tol(g["e%d_z_var" % e], ost["c"], ost["sn"])), name
         # mean: an ill-conditioned sum -> error measured against sum |k_i alpha_i|
         scale = pc_scale(ost, Xin)
         assert np.max(np.abs(zm - g["e%d_z_mean" % e]) / scale) <= 1e-13, name
         om, ov = orc.pc_predict(ost, Xin)
-        assert rel_err(zv, ov) <= REL
+        assert np.all(np.abs(zv - ov) <= var_tol(ov, ost["c"], ost["sn"])), name
         assert np.max(np.abs(zm - om) / scale) <= 1e-13
 
 
@@ -49,21 +49,22 @@ def test_emulator_predict(case):
     """boundary #1: Emulator.predict(X, return_cov=True, extra_std=arr) (kernels (a)+(b))."""
     from gpbt_b200.emulator import Emulator
     name, g, states, sts = case
+    REL_G, _ = golden_tol(name)
     Xin = g["X"][g["inside"]]
     for e, st in enumerate(states):
         emu = Emulator.from_state(st)
         rows = g["e%d_mean_x" % e].shape[0]
         mean, cov = emu.predict(Xin[:rows], return_cov=True, extra_std=g["extra_std"][:rows])
-        assert rel_err(mean, g["e%d_mean_x" % e]) <= REL, name
+        assert rel_err(mean, g["e%d_mean_x" % e]) <= REL_G, name
         ref = g["e%d_cov_x" % e]
-        assert scaled_err(cov, ref) <= REL, name
+        assert scaled_err(cov, ref) <= REL_G, name
         d = np.arange(ref.shape[1])
-        assert rel_err(cov[:, d, d], ref[:, d, d]) <= REL, name
+        assert rel_err(cov[:, d, d], ref[:, d, d]) <= REL_G, name
         assert np.array_equal(cov, np.swapaxes(cov, 1, 2)) or scaled_err(cov, np.swapaxes(cov, 1, 2)) < 1e-15
         mean0 = emu.predict(Xin[:256], return_cov=False)
-        assert rel_err(mean0, g["e%d_mean0" % e]) <= REL, name
+        assert rel_err(mean0, g["e%d_mean0" % e]) <= REL_G, name
         md, vd = emu.predict_diag(Xin[:rows], extra_std=g["extra_std"][:rows])
-        assert rel_err(md, g["e%d_mean_x" % e]) <= REL and rel_err(vd, ref[:, d, d]) <= REL, name
+        assert rel_err(md, g["e%d_mean_x" % e]) <= REL_G and rel_err(vd, ref[:, d, d]) <= REL_G, name
         # scalar extra_std (the reference's default 0 breaks on NumPy 2; ours must not)
         # (a 4-row call uses a narrower walker tile than the 256-row one: same values up to
         # summation order)
@@ -76,12 +77,13 @@ def test_chain_predict_and_mvn(case):
     from gpbt_b200.device import DeviceChain, mvn_loglike_batch
     from gpbt_b200.mcmc import mvn_loglike
     name, g, states, sts = case
+    REL_G, _ = golden_tol(name)
     ch = DeviceChain(states, g["lo"], g["hi"], g["y_exp"].reshape(-1), g["cov_exp"])
     Xin = g["X"][g["inside"]]
     rows = g["chain_mean"].shape[0]
     mean, cov = ch.predict(Xin[:rows], 0.0)
-    assert rel_err(mean, g["chain_mean"]) <= REL, name
-    assert scaled_err(cov, g["chain_cov"]) <= REL, name
+    assert rel_err(mean, g["chain_mean"]) <= REL_G, name
+    assert scaled_err(cov, g["chain_cov"]) <= REL_G, name
     assert np.array_equal(cov == 0.0, g["chain_cov"] == 0.0) or len(states) == 1
     dY = g["chain_mean"] - g["y_exp"]
     C = g["chain_cov"] + g["cov_exp"]
@@ -100,6 +102,7 @@ def test_log_posterior(case, path):
     """boundary #2: Chain.log_posterior / log_likelihood values and out-of-bounds conventions."""
     from gpbt_b200.device import DeviceChain
     name, g, states, sts = case
+    _, ABS_G = golden_tol(name)
     ch = DeviceChain(states, g["lo"], g["hi"], g["y_exp"].reshape(-1), g["cov_exp"])
     diag_ok = all(s.no_pca or s.exp_diag for s in states)
     if (path == "lowrank" and ch.lowrank is None) or (path == "diag" and not diag_ok):
@@ -113,19 +116,16 @@ def test_log_posterior(case, path):
     fin = np.isfinite(ref)
     lp = ch.log_target(g["X"], -np.inf, path=path)
     assert np.array_equal(np.isneginf(lp), np.isneginf(ref)), name
-    if "e0_Lpacked" in g:
-        assert np.max(np.abs(lp[fin] - ref[fin])) <= ABS_LP, (name, path)
-    else:
-        # config 2: the golden file carries the reference's hyper-parameters and alpha_ but not its
-        # 40 MB of L_, which is rebuilt here with this machine's LAPACK.  A last-bit difference in L_
-        # moves the predictive variances by ~1e-11 relative and log L (|log L| ~ 400) by a few 1e-9 --
-        # on the reference itself just as well.  So: 1e-8 against the oracle ON THE SAME STATE (the
-        # parity statement), and the golden of the reference within twice that.
+    # north-star tolerance against the reference's own golden vector, every case.  (Config 2's golden file
+    # carries the reference's hyper-parameters and alpha_ but not its 40 MB of L_, which is rebuilt here with
+    # this machine's LAPACK: a last-bit difference in L_ moves log L, |log L| ~ 400, by a few 1e-9 -- measured
+    # 5.2e-9 on the GPU box, inside the tolerance; the oracle ON THE SAME STATE is checked as well.)
+    assert np.max(np.abs(lp[fin] - ref[fin])) <= ABS_G, (name, path)
+    if "e0_Lpacked" not in g:
         rows = np.flatnonzero(fin)[:200]
         want = orc.log_posterior(sts, g["X"][rows], g["lo"], g["hi"], g["y_exp"], g["cov_exp"])
-        assert np.max(np.abs(lp[rows] - want)) <= ABS_LP, (name, path)
-        assert np.max(np.abs(lp[fin] - ref[fin])) <= 2 * ABS_LP, (name, path)
-    tol = ABS_LP if "e0_Lpacked" in g else 2 * ABS_LP
+        assert np.max(np.abs(lp[rows] - want)) <= ABS_G, (name, path)
+    tol = ABS_G
     lf = ch.log_target(g["X"], -1e300, path=path)
     assert np.array_equal(lf == -1e300, g["lp_like_finite"] == -1e300)
     assert np.max(np.abs(lf[fin] - g["lp_like_finite"][fin])) <= tol
@@ -556,3 +556,78 @@ def test_cholesky_variants_agree(m):
             assert np.isneginf(got[5]) and np.max(np.abs(np.delete(got, 5) - np.delete(want, 5))) <= ABS_LP, which
     finally:
         _lib.set_option("chol", None)
+
+
+@pytest.mark.parametrize("name", ["c1_rbf", "odd_shape", "c1_multi", "c2_rbf"])
+def test_fused_cholesky_path(name):
+    """Dense path with kernels (b) + (c) fused (chol_fused.cuh: the covariance tiles are generated inside the
+    panel-synchronous Cholesky, nothing of size N m^2 is stored) against the reference's golden vectors, the
+    oracle and the other paths: one diagonal block (m = 13), a partial last panel (m = 50, 300), several
+    emulators, a full (coupling) experimental covariance, out-of-bounds rows, any sub-batch / stream split."""
+    from gpbt_b200 import _lib
+    from gpbt_b200.device import DeviceChain
+    if name not in goldens.available():
+        pytest.skip("golden %s not present" % name)
+    g = goldens.load(name)
+    states, sts = product_states(g)
+    ch = DeviceChain(states, g["lo"], g["hi"], g["y_exp"].reshape(-1), g["cov_exp"])
+    ref = g["lp_posterior"]
+    fin = np.isfinite(ref)
+    try:
+        _lib.set_option("chol", "fused")
+        lp = ch.log_target(g["X"], -np.inf, path="dense")
+        assert np.array_equal(np.isneginf(lp), np.isneginf(ref)) and ch.last_notpd == 0
+        assert np.max(np.abs(lp[fin] - ref[fin])) <= ABS_LP, name
+        # more rows than the golden file has, ragged, with rows outside the box; -1e300 convention
+        rng = np.random.default_rng(11)
+        X = rng.uniform(g["lo"], g["hi"], (777, len(g["lo"])))
+        X[::29, -1] = g["lo"][-1] - 0.5
+        want = ch.log_target(X, -1e300, path="lowrank")
+        base = ch.log_target(X, -1e300, path="dense")
+        assert np.all(base[::29] == -1e300) and np.max(np.abs(base - want)) <= ABS_LP
+        rows = np.flatnonzero(base > -1e299)[:40]
+        wo = orc.log_posterior(sts, X[rows], g["lo"], g["hi"], g["y_exp"], g["cov_exp"])
+        assert np.max(np.abs(base[rows] - wo)) <= ABS_LP
+        # the split into sub-batches and streams is invisible in the numbers
+        for batch, streams in ((64, 1), (128, 3), (100000, 2)):
+            _lib.set_option("chol_batch", batch)
+            _lib.set_option("chol_streams", streams)
+            np.testing.assert_array_equal(ch.log_target(X, -1e300, path="dense"), base)
+        _lib.set_option("chol_batch", None)
+        _lib.set_option("chol_streams", None)
+        # a full experimental covariance (couples the emulators of c1_multi): still the fused kernels
+        cov_sys = goldens.cov_exp_sys(g)
+        ch2 = DeviceChain(states, g["lo"], g["hi"], g["y_exp"].reshape(-1), cov_sys)
+        lps = ch2.log_target(g["X"], -np.inf, path="dense")
+        wo = orc.log_posterior(sts, g["X"][fin][:60], g["lo"], g["hi"], g["y_exp"], cov_sys)
+        assert np.max(np.abs(lps[fin][:60] - wo)) <= ABS_LP
+        if "lp_posterior_sys" in g:
+            assert np.max(np.abs(lps[fin] - g["lp_posterior_sys"][fin])) <= ABS_LP
+        ch2.release()
+    finally:
+        for k in ("chol", "chol_batch", "chol_streams"):
+            _lib.set_option(k, None)
+    ch.release()
+
+
+def test_fused_cholesky_not_positive_definite():
+    """walkers whose covariance is not positive definite get the out-of-bounds value and are counted, the
+    others are unaffected (fused path; the reference's own check is broken, src/mcmc.py:44-54)"""
+    from gpbt_b200 import _lib
+    from gpbt_b200.device import DeviceChain
+    g = goldens.load("c1_rbf")
+    states, sts = product_states(g)
+    cov = g["cov_exp"].copy()
+    cov[7, 7] = -50.0                      # indefinite whatever the emulator adds
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ch = DeviceChain(states, g["lo"], g["hi"], g["y_exp"].reshape(-1), cov)
+    try:
+        _lib.set_option("chol", "fused")
+        lp = ch.log_target(g["X"], -np.inf, path="dense")
+        inside = np.isfinite(g["lp_posterior"])
+        assert np.all(np.isneginf(lp)) and ch.last_notpd == int(inside.sum())
+    finally:
+        _lib.set_option("chol", None)
+    ch.release()

@@ -7,7 +7,9 @@ rows = list(csv.reader(open(sys.argv[1])))
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
 hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hdr_i]
-body = [r for r in rows[hdr_i + 1:] if len(r) == len(hdr)]
+# (a dump may hold several views -- SASS, then source -- each with its own header: take the first)
+end = next((i for i in range(hdr_i + 1, len(rows)) if rows[i] and rows[i][0] in ("Address", "Kernel Name", "#")), len(rows))
+body = [r for r in rows[hdr_i + 1:end] if len(r) == len(hdr)]
 col = {h: i for i, h in enumerate(hdr)}
 stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
 tot = {s: 0 for s in stalls}
