@@ -24,7 +24,7 @@ SYMBOLS = [
     "gpbt_ensemble_run", "gpbt_ensemble_steps", "gpbt_ensemble_reserve",
     "gpbt_ensemble_prepare", "gpbt_ensemble_begin_half", "gpbt_ensemble_copy_proposals", "gpbt_ensemble_end_half", "gpbt_ensemble_read", "gpbt_ensemble_reset",
     "gpbt_device_count", "gpbt_set_device", "gpbt_get_device", "gpbt_set_option",
-    "gpbt_debug_timing_read", "gpbt_fanout_create", "gpbt_fanout_destroy", "gpbt_fanout_size", "gpbt_fanout_log_posterior_host",
+    "gpbt_debug_timing_read", "gpbt_debug_fused_read", "gpbt_fanout_create", "gpbt_fanout_destroy", "gpbt_fanout_size", "gpbt_fanout_log_posterior_host",
 ]
 
 
@@ -76,6 +76,7 @@ def _load():
     lib.gpbt_ensemble_read.argtypes = [vp, i64, i64, dp, dp, dp, dp]
     lib.gpbt_ensemble_reset.argtypes = [vp]
     lib.gpbt_debug_timing_read.argtypes = [vp, i64]
+    lib.gpbt_debug_fused_read.argtypes = [vp, i32, i64, dp, i64]
     lib.gpbt_device_count.argtypes = []
     lib.gpbt_set_device.argtypes = [i32]
     lib.gpbt_get_device.argtypes = []

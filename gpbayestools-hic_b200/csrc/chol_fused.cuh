@@ -33,6 +33,11 @@ constexpr int kCfStages = 3;     // ring depth, 16 columns per stage
 constexpr int kCfLd = kSpLd;     // row stride of 32-column tiles in shared memory
 constexpr int kCfLdD = 34;       // row stride of the diagonal block in the factor kernel (lane = row, LDS.128 pairs)
 
+// Everything one launch of the chain hands to the next (Dinv, raw blocks, t, log-determinants, flags) and
+// what kernel (a) / the mean kernel produced in the same call is read with ld.global.cg (L2) or by the
+// async copies, never through L1: with sub-batches on several streams an SM is never idle between two
+// launches of a chain, its L1 is not invalidated, and a plain load can return a line cached before another
+// SM rewrote it (observed: a few walkers per thousand off by O(1) in log L with two streams).
 struct CholFusedParams {
   const double* __restrict__ Fp;     // packed panels of F (layout of the factor), rows >= M and columns >= M zero
   const double* __restrict__ Fd;     // [nP][32][32] diagonal blocks of F, identity padded
@@ -53,6 +58,7 @@ struct CholFusedParams {
   double notpd_value, add_const;
   int64_t N, Lstride, ldz;
   int M, Mg, Q, Qp;
+  int flags;                         // debugging: 1 = wait for the predecessor first thing
   long long* dbg;                    // null, or [16 launches][32 walkers][8 tiles][8] clock64 stamps (tuning)
 };
 
@@ -132,7 +138,8 @@ __global__ void __launch_bounds__(kCfThreads, 4) chol_fused_panel_kernel(const C
     // launch only after ITS wait, i.e. once the previous panel launch has completed -- so the factor
     // panels < J, z_var and skip are final.  Only Dinv_J (and t[J:J+32] in tile 0) are still being written:
     // the wait sits in front of their first use, and the operand stream overlaps the factor kernel.
-    if (prm.skip != nullptr && prm.skip[w]) return;
+    if (prm.flags & 1) pdl_wait_prior_grids();
+    if (prm.skip != nullptr && __ldcg(prm.skip + w)) return;
     __syncthreads();   // barriers initialised
 
     // operand stage s = columns 16 s .. 16 s + 15 = sub-blocks (2 s, 2 s + 1) mod 4 of panel s / 2
@@ -161,7 +168,7 @@ __global__ void __launch_bounds__(kCfThreads, 4) chol_fused_panel_kernel(const C
     if (active) {
       const double* zv = prm.z_var + w * prm.ldz;
       for (int k0 = 0; k0 < Qp; k0 += 4) {
-        const double vk = (k0 + t < prm.Q) ? zv[k0 + t] : 0.0;
+        const double vk = (k0 + t < prm.Q) ? __ldcg(zv + k0 + t) : 0.0;
         double a[2], b[4];
 #pragma unroll
         for (int mb = 0; mb < 2; mb++) a[mb] = vk * __ldg(prm.UT + (size_t)(r0 + 16 * warp + 8 * mb + g) * Qp + k0 + t);
@@ -173,10 +180,13 @@ __global__ void __launch_bounds__(kCfThreads, 4) chol_fused_panel_kernel(const C
           for (int nbk = 0; nbk < 4; nbk++) dmma884(acc[mb][nbk][0], acc[mb][nbk][1], a[mb], b[nbk]);
       }
     }
-    // No block-wide barrier in the stream: a warp that is done with a stage arrives on its "empty"
-    // barrier; warp 0 refills the slot of stage s - 1 once all four have (it has just finished stage s
-    // itself, so that wait is normally over) -- the warps drift apart by up to a stage instead of meeting
-    // at every one.
+    // No block-wide barrier in the stream: a warp that is done with a stage arrives on its "empty" barrier
+    // and goes on; only warp 0 waits -- until all four have finished stage s -- before it refills the slot
+    // of stage s - 1 with stage s + 2.  (Refilling as soon as everybody had finished stage s - 1, i.e. while
+    // some warp was still inside stage s, corrupted about 3 walkers per million whenever kernels of another
+    // stream shared the SM -- 8..41 of 4.9 M evaluations, 0 of 9.8 M with this wait, 0 of 20 M with a block
+    // barrier per stage; tools/r02/fused_verify.py.  The protocol reads correct either way; the cause was not
+    // found, the measured-safe order is kept.)
 #pragma unroll 1
     for (int s = 0; s < nst; s++) {
       mbar_wait(&full_bar[s % kCfStages], (s / kCfStages) & 1);
@@ -206,7 +216,7 @@ __global__ void __launch_bounds__(kCfThreads, 4) chol_fused_panel_kernel(const C
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[s % kCfStages]);
       if (warp == 0 && s + kCfStages - 1 < nst) {
-        if (s >= 1) mbar_wait(&empty_bar[(s - 1) % kCfStages], ((s - 1) / kCfStages) & 1);
+        mbar_wait(&empty_bar[s % kCfStages], (s / kCfStages) & 1);   // all four warps are done with stage s
         issue(s + kCfStages - 1);
       }
     }
@@ -288,8 +298,8 @@ __global__ void __launch_bounds__(kCfThreads, 4) chol_fused_panel_kernel(const C
   }
   cf_stamp(prm, J, w, 0);
   pdl_launch_dependents();
-  if (!has_panel) pdl_wait_prior_grids();   // the prologue launch follows kernels outside the chain (z_var, mean, skip)
-  if (prm.skip != nullptr && prm.skip[w]) return;
+  if (!has_panel || (prm.flags & 1)) pdl_wait_prior_grids();   // the prologue launch follows kernels outside the chain (z_var, mean, skip)
+  if (prm.skip != nullptr && __ldcg(prm.skip + w)) return;
   __syncthreads();
 
   auto issue0 = [&](int s) {
@@ -316,14 +326,14 @@ __global__ void __launch_bounds__(kCfThreads, 4) chol_fused_panel_kernel(const C
   if (has_panel) {
     // t[:J] is final (see the note on the wait in the regular tile); t[J:J+32] follows after the wait
     const double* tw = prm.tvec + (size_t)w * Mg;
-    for (int k = tid; k < J; k += kCfThreads) tvs[k] = tw[k];
+    for (int k = tid; k < J; k += kCfThreads) tvs[k] = __ldcg(tw + k);
   }
   // the forward solve's right-hand side  y[rows] - L[rows, :Jd] t[:Jd]: thread (row rr, part) takes a
   // quarter of the columns of every stage
   const int rr = tid >> 2, part = tid & 3;
   double yrow = 0.0, racc = 0.0;
   if (part == 0 && rr < nb) {
-    yrow = prm.mean[w * M + Jd + rr];
+    yrow = __ldcg(prm.mean + w * M + Jd + rr);
     if (prm.y_exp) yrow -= prm.y_exp[Jd + rr];
   }
   {
@@ -331,7 +341,7 @@ __global__ void __launch_bounds__(kCfThreads, 4) chol_fused_panel_kernel(const C
     const double* zv = prm.z_var + w * prm.ldz;
     const int row = min(Jd + 8 * warp + g, Mg - 1);
     for (int k0 = 0; k0 < Qp; k0 += 4) {
-      const double vk = (k0 + t < prm.Q) ? zv[k0 + t] : 0.0;
+      const double vk = (k0 + t < prm.Q) ? __ldcg(zv + k0 + t) : 0.0;
       const double a = vk * __ldg(prm.UT + (size_t)row * Qp + k0 + t);
 #pragma unroll
       for (int nbk = 0; nbk < 4; nbk++) {
@@ -377,7 +387,7 @@ __global__ void __launch_bounds__(kCfThreads, 4) chol_fused_panel_kernel(const C
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[s % kCfStages]);
     if (warp == 0 && s + kCfStages - 1 < nst) {
-      if (s >= 1) mbar_wait(&empty_bar[(s - 1) % kCfStages], ((s - 1) / kCfStages) & 1);
+      mbar_wait(&empty_bar[s % kCfStages], (s / kCfStages) & 1);   // (see the regular tile)
       issue0(s + kCfStages - 1);
     }
   }
@@ -390,7 +400,7 @@ __global__ void __launch_bounds__(kCfThreads, 4) chol_fused_panel_kernel(const C
       cp_async16(Dv + r * kCfLd + 2 * c2, dw + r * kCfNB + 2 * c2);
     }
     cp_async_commit();
-    if (tid < kCfNB) tvs[J + tid] = prm.tvec[(size_t)w * Mg + J + tid];
+    if (tid < kCfNB) tvs[J + tid] = __ldcg(prm.tvec + (size_t)w * Mg + J + tid);
   }
   cp_async_wait<0>();
   __syncthreads();   // Dinv_J and t have landed; the ring is free
@@ -492,7 +502,7 @@ __global__ void __launch_bounds__(kCfFactorWarps * 32) chol_fused_factor_kernel(
   if (wi >= n_walkers) return;
   stamp(1);
   const int64_t w = w_first + wi;
-  if (prm.skip != nullptr && prm.skip[w]) return;
+  if (prm.skip != nullptr && __ldcg(prm.skip + w)) return;
   const int M = prm.M, Mg = prm.Mg;
   const int nb = min(kCfNB, M - Jd);
   const bool first = Jd == 0, is_last = Jd + kCfNB >= M;
@@ -502,8 +512,8 @@ __global__ void __launch_bounds__(kCfFactorWarps * 32) chol_fused_factor_kernel(
     // all 8 KB of the block in flight at once (16 coalesced 16-byte loads per lane), then to shared memory
     double2 v[16];
 #pragma unroll
-    for (int i = 0; i < 16; i++) v[i] = *reinterpret_cast<const double2*>(dr + 2 * (lane + 32 * i));
-    const double rv = lane < nb ? prm.tvec[(size_t)w * Mg + Jd + lane] : 0.0;
+    for (int i = 0; i < 16; i++) v[i] = __ldcg(reinterpret_cast<const double2*>(dr + 2 * (lane + 32 * i)));
+    const double rv = lane < nb ? __ldcg(prm.tvec + (size_t)w * Mg + Jd + lane) : 0.0;
 #pragma unroll
     for (int i = 0; i < 16; i++) {
       const int idx = 2 * (lane + 32 * i);
@@ -581,9 +591,9 @@ __global__ void __launch_bounds__(kCfFactorWarps * 32) chol_fused_factor_kernel(
   }
   const double q2 = warp_sum(sx * sx);
   if (lane == 0) {
-    const double ld = (first ? 0.0 : prm.logdet[w]) + lsum;
-    const double tot = (first ? 0.0 : prm.tsq[w]) + q2;
-    const int bad = (first ? 0 : prm.bad[w]) | bad_now;
+    const double ld = (first ? 0.0 : __ldcg(prm.logdet + w)) + lsum;
+    const double tot = (first ? 0.0 : __ldcg(prm.tsq + w)) + q2;
+    const int bad = (first ? 0 : __ldcg(prm.bad + w)) | bad_now;
     if (!is_last) {
       prm.logdet[w] = ld;
       prm.tsq[w] = tot;

@@ -762,6 +762,25 @@ __global__ void debug_exp_neg_kernel(const double* __restrict__ x, double* __res
   if (i < n) y[i] = exp_neg(x[i], tab);
 }
 
+extern "C" int gpbt_debug_fused_read(gpbt_chain_t ch, int what, int64_t w, double* dst_host, int64_t count) {
+  if (!ch || !dst_host || w < 0 || count < 0) return fail(GPBT_EINVAL, "gpbt_debug_fused_read: bad argument");
+  const double* src = nullptr;
+  switch (what) {
+    case 0: src = ch->cf_L + (size_t)w * ch->Lstride; break;
+    case 1: src = ch->cf_tvec + (size_t)w * ch->Mg; break;
+    case 2: src = ch->cf_dinv + (size_t)w * 1024; break;
+    case 3: src = ch->cf_draw + (size_t)w * 1024; break;
+    case 4: src = ch->z_var + (size_t)w * ch->Q; break;
+    case 5: src = ch->cf_mean + (size_t)w * ch->M; break;
+    case 6: src = ch->cf_logdet + w; break;
+    case 7: src = ch->cf_tsq + w; break;
+    default: return fail(GPBT_EINVAL, "gpbt_debug_fused_read: unknown buffer %d", what);
+  }
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(dst_host, src, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 extern "C" int gpbt_debug_timing_read(void* dst_host, int64_t bytes) {
   if (!dst_host || bytes < 0 || (size_t)bytes > kCfDbgBytes) return fail(GPBT_EINVAL, "gpbt_debug_timing_read: bad argument");
   if (!g_cf_dbg) return fail(GPBT_EINVAL, "gpbt_debug_timing_read: nothing recorded (option cf_debug)");
@@ -1107,7 +1126,8 @@ int run_chol_fused(gpbt_chain* ch, double* lp, int* n_notpd, double notpd_value,
   prm.notpd_value = notpd_value; prm.add_const = kSysConst; prm.N = N; prm.Lstride = ch->Lstride; prm.ldz = ch->Q;
   prm.M = ch->M; prm.Mg = ch->Mg; prm.Q = ch->Q; prm.Qp = ch->Qp;
   prm.dbg = nullptr;
-  if (g_opt.cf_debug.load()) {
+  prm.flags = g_opt.cf_debug.load() >> 4;      // (cf_debug = 16 * flags + record-stamps bit)
+  if (g_opt.cf_debug.load() & 1) {
     if (!g_cf_dbg) CU(cudaMallocManaged(&g_cf_dbg, kCfDbgBytes));
     prm.dbg = g_cf_dbg;
   }
@@ -1142,6 +1162,14 @@ int run_chol_fused(gpbt_chain* ch, double* lp, int* n_notpd, double notpd_value,
     cudaStream_t sb = (b % n_streams == 0) ? st : ch->cf_streams[b % n_streams];
     for (int J = -kCfNB; J + kCfNB < Mg; J += kCfNB) {
       const int tiles = (J >= 0 && Mg > J + 2 * kCfNB) ? (Mg - J - 2 * kCfNB + kCfRows - 1) / kCfRows : 0;
+      if (prm.flags & 4) {   // plain stream order, no programmatic launch
+        chol_fused_panel_kernel<<<dim3((unsigned)(1 + tiles), (unsigned)nw), kCfThreads, smem, sb>>>(prm, J, w0);
+        LAUNCH_CHECK();
+        chol_fused_factor_kernel<<<dim3((unsigned)((nw + kCfFactorWarps - 1) / kCfFactorWarps)), kCfFactorWarps * 32,
+                                   kCfFactorSmem, sb>>>(prm, J + kCfNB, w0, nw);
+        LAUNCH_CHECK();
+        continue;
+      }
       CU(launch_pdl(chol_fused_panel_kernel, dim3((unsigned)(1 + tiles), (unsigned)nw), kCfThreads, smem, sb, prm, J, w0));
       LAUNCH_CHECK();
       CU(launch_pdl(chol_fused_factor_kernel, dim3((unsigned)((nw + kCfFactorWarps - 1) / kCfFactorWarps)),

@@ -289,6 +289,9 @@ int gpbt_debug_exp_neg(const double* x_dev, double* y_dev, int64_t n, void* stre
 /* tuning hook: with option "cf_debug" the fused Cholesky records clock64 stamps of its phases for the
  * first 32 walkers, [16 launches][32 walkers][8 tiles][8 stamps] int64; this copies them out        */
 int gpbt_debug_timing_read(void* dst_host, int64_t bytes);
+/* tuning / debugging hook: work buffers of the fused Cholesky of walker w of the last dense call
+ * (what: 0 factor panels, 1 t, 2 Dinv, 3 raw diagonal block, 4 z_var, 5 mean, 6 log det, 7 |t|^2)   */
+int gpbt_debug_fused_read(gpbt_chain_t chain, int what, int64_t w, double* dst_host, int64_t count);
 
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches)      */
 int64_t gpbt_launch_count(void);
