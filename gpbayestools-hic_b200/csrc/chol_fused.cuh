@@ -349,8 +349,10 @@ __global__ void __launch_bounds__(kCfThreads, 4) chol_fused_panel_kernel(const C
           const double bp = __ldg(prm.UT + (size_t)(J + 8 * nbk + g) * Qp + k0 + t);
           dmma884(accp[nbk][0], accp[nbk][1], a, bp);
         }
-        const double bd = __ldg(prm.UT + (size_t)min(Jd + 8 * nbk + g, Mg - 1) * Qp + k0 + t);
-        dmma884(accd[nbk][0], accd[nbk][1], a, bd);
+        if (nbk <= warp) {
+          const double bd = __ldg(prm.UT + (size_t)min(Jd + 8 * nbk + g, Mg - 1) * Qp + k0 + t);
+          dmma884(accd[nbk][0], accd[nbk][1], a, bd);
+        }
       }
     }
   }
@@ -363,21 +365,22 @@ __global__ void __launch_bounds__(kCfThreads, 4) chol_fused_panel_kernel(const C
 #pragma unroll
     for (int sub = 0; sub < 2; sub++) {
       const double2 a = *reinterpret_cast<const double2*>(A + ((size_t)sub * kCfNB + 8 * warp + g) * 8 + 2 * t);
+      // (of the diagonal block only the lower triangle is needed: column blocks nbk <= warp)
       double2 bp[4], bd[4];
 #pragma unroll
       for (int nbk = 0; nbk < 4; nbk++) {
         bp[nbk] = *reinterpret_cast<const double2*>(B + ((size_t)sub * kCfNB + 8 * nbk + g) * 8 + 2 * t);
-        bd[nbk] = *reinterpret_cast<const double2*>(A + ((size_t)sub * kCfNB + 8 * nbk + g) * 8 + 2 * t);
+        if (nbk <= warp) bd[nbk] = *reinterpret_cast<const double2*>(A + ((size_t)sub * kCfNB + 8 * nbk + g) * 8 + 2 * t);
       }
 #pragma unroll
       for (int nbk = 0; nbk < 4; nbk++) {
         dmma884(accp[nbk][0], accp[nbk][1], -a.x, bp[nbk].x);
-        dmma884(accd[nbk][0], accd[nbk][1], -a.x, bd[nbk].x);
+        if (nbk <= warp) dmma884(accd[nbk][0], accd[nbk][1], -a.x, bd[nbk].x);
       }
 #pragma unroll
       for (int nbk = 0; nbk < 4; nbk++) {
         dmma884(accp[nbk][0], accp[nbk][1], -a.y, bp[nbk].y);
-        dmma884(accd[nbk][0], accd[nbk][1], -a.y, bd[nbk].y);
+        if (nbk <= warp) dmma884(accd[nbk][0], accd[nbk][1], -a.y, bd[nbk].y);
       }
       const double2 lv = *reinterpret_cast<const double2*>(A + ((size_t)sub * kCfNB + rr) * 8 + 2 * part);
       const double2 tv2 = *reinterpret_cast<const double2*>(tvs + 16 * s + 8 * sub + 2 * part);
@@ -443,11 +446,14 @@ __global__ void __launch_bounds__(kCfThreads, 4) chol_fused_panel_kernel(const C
       const double2 a2 = *reinterpret_cast<const double2*>(&T[(8 * warp + g) * kCfLd + 8 * kk + 2 * t]);
       double2 b[4];
 #pragma unroll
-      for (int nbk = 0; nbk < 4; nbk++) b[nbk] = *reinterpret_cast<const double2*>(&T[(8 * nbk + g) * kCfLd + 8 * kk + 2 * t]);
+      for (int nbk = 0; nbk < 4; nbk++)
+        if (nbk <= warp) b[nbk] = *reinterpret_cast<const double2*>(&T[(8 * nbk + g) * kCfLd + 8 * kk + 2 * t]);
 #pragma unroll
-      for (int nbk = 0; nbk < 4; nbk++) dmma884(accd[nbk][0], accd[nbk][1], -a2.x, b[nbk].x);
+      for (int nbk = 0; nbk < 4; nbk++)
+        if (nbk <= warp) dmma884(accd[nbk][0], accd[nbk][1], -a2.x, b[nbk].x);
 #pragma unroll
-      for (int nbk = 0; nbk < 4; nbk++) dmma884(accd[nbk][0], accd[nbk][1], -a2.y, b[nbk].y);
+      for (int nbk = 0; nbk < 4; nbk++)
+        if (nbk <= warp) dmma884(accd[nbk][0], accd[nbk][1], -a2.y, b[nbk].y);
     }
 #pragma unroll
     for (int c = 0; c < 8; c++) racc = fma(T[rr * kCfLd + 8 * part + c], tvs[J + 8 * part + c], racc);
@@ -482,15 +488,18 @@ __global__ void __launch_bounds__(kCfThreads, 4) chol_fused_panel_kernel(const C
 //   raw block D (written by tile 0) -> factor and inverse (register factorisation, see below);  Dinv to the
 //   work buffer, t[Jd:Jd+32] = Dinv rhs, log-determinant, |t|^2; the last block emits lp[w].
 constexpr int kCfFactorWarps = 4;
-constexpr size_t kCfFactorSmem = sizeof(double) * kCfFactorWarps * (2 * kCfNB * kCfLdD + kCfNB);
+constexpr size_t kCfFactorSmem = sizeof(double) * kCfFactorWarps * (kCfNB * kCfLdD + kCfNB);
 
 __global__ void __launch_bounds__(kCfFactorWarps * 32) chol_fused_factor_kernel(const CholFusedParams prm, int Jd,
                                                                                  int64_t w_first, int64_t n_walkers) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double* D = reinterpret_cast<double*>(smem_raw) + (size_t)warp * (2 * kCfNB * kCfLdD + kCfNB);   // [32][34] block -> factor
-  double* Dn = D + kCfNB * kCfLdD;                                                                 // [32][34] inverse of the factor
-  double* red = Dn + kCfNB * kCfLdD;                                                               // [32] right-hand side
+  // ONE 32x34 tile per walker (24 warps = walkers per SM): its four 16x16 blocks are reused as the
+  // factorisation proceeds --  D11 -> L11 -> (dead) -> I22;   D12 (never an input) <- I11;
+  // D21 -> L21 -> M = L21 I11 -> Dinv21 = -I22 M;   D22 -> D22 - L21 L21^T -> L22.
+  double* D = reinterpret_cast<double*>(smem_raw) + (size_t)warp * (kCfNB * kCfLdD + kCfNB);
+  double* red = D + kCfNB * kCfLdD;                                                                // [32] right-hand side
+  double* B11 = D, *B12 = D + 16, *B21 = D + 16 * kCfLdD, *B22 = D + 16 * kCfLdD + 16;
   const int64_t wi = (int64_t)blockIdx.x * kCfFactorWarps + warp;
   auto stamp = [&](int slot) {
     if (prm.dbg != nullptr && lane == 0 && w_first + wi < 32)
@@ -537,8 +546,8 @@ __global__ void __launch_bounds__(kCfFactorWarps * 32) chol_fused_factor_kernel(
   for (int blk = 0; blk < 2; blk++) {
     const int o = 16 * blk;
     if (blk == 1) {
-      tile16_mma<true>(D + 16 * kCfLdD, Dn, nullptr, D + 16 * kCfLdD, 1.0, g, t);
-      tile16_mma<true>(D + 16 * kCfLdD, D + 16 * kCfLdD, D + 16 * kCfLdD + 16, D + 16 * kCfLdD + 16, -1.0, g, t);
+      tile16_mma<true>(B21, B12, nullptr, B21, 1.0, g, t);      // L21 = D21 I11^T
+      tile16_mma<true>(B21, B21, B22, B22, -1.0, g, t);         // D22 -= L21 L21^T
     }
     double S[16];
 #pragma unroll
@@ -560,33 +569,55 @@ __global__ void __launch_bounds__(kCfFactorWarps * 32) chol_fused_factor_kernel(
     }
     if (lane < 16 && o + lane < nb) lsum += log(piv);
     __syncwarp();
-    if (lane < 16) {
+    // the inverse of this block's factor (identity rows, lanes 16-31): I11 -> B12, I22 -> B11 (L11 is
+    // dead by then); the factor itself is only needed for L22's ... nothing: L11 and L22 are not stored
+    double* Iout = blk == 0 ? B12 : B11;
+    if (lane >= 16) {
 #pragma unroll
-      for (int c = 0; c < 16; c++) D[(o + r) * kCfLdD + o + c] = (c <= r) ? S[c] : 0.0;
-    } else {
-#pragma unroll
-      for (int c = 0; c < 16; c++) Dn[(o + c) * kCfLdD + o + r] = (c >= r) ? S[c] : 0.0;
+      for (int c = 0; c < 16; c++) Iout[c * kCfLdD + r] = (c >= r) ? S[c] : 0.0;
     }
     __syncwarp();
   }
   stamp(3);
-  tile16_mma<false>(D + 16 * kCfLdD, Dn, nullptr, Dn + 16, 1.0, g, t);                        // M = L21 I11
-  tile16_mma<false>(Dn + 16 * kCfLdD + 16, Dn + 16, nullptr, Dn + 16 * kCfLdD, -1.0, g, t);   // -I22 M
-  for (int idx = lane; idx < 256; idx += 32) Dn[(idx >> 4) * kCfLdD + 16 + (idx & 15)] = 0.0;
-  __syncwarp();
+  tile16_mma<false>(B21, B12, nullptr, B21, 1.0, g, t);     // M = L21 I11       (in place)
+  tile16_mma<false>(B11, B21, nullptr, B21, -1.0, g, t);    // Dinv21 = -I22 M   (in place)
+  // Dinv = [[I11 (B12), 0], [Dinv21 (B21), I22 (B11)]]
   stamp(4);
   lsum = warp_sum(lsum);                // sum of log(pivot) = log det of the block
   const int bad_now = pd ? 0 : 1;
   if (!is_last) {
+    // lane -> (row parity, column pair): rows 2i + (lane >> 4), columns 2 (lane & 15), +1
+    const int col = 2 * (lane & 15), cl = col & 15, hi = lane >> 4;
 #pragma unroll
     for (int i = 0; i < 16; i++) {
-      const int idx = 2 * (lane + 32 * i);
-      *reinterpret_cast<double2*>(dw + idx) = *reinterpret_cast<const double2*>(&Dn[(idx >> 5) * kCfLdD + (idx & 31)]);
+      const int row = 2 * i + hi;
+      double2 v = make_double2(0.0, 0.0);
+      if (i < 8) {
+        if (col < 16) v = *reinterpret_cast<const double2*>(&B12[row * kCfLdD + cl]);
+      } else {
+        v = *reinterpret_cast<const double2*>(&(col < 16 ? B21 : B11)[(row - 16) * kCfLdD + cl]);
+      }
+      *reinterpret_cast<double2*>(dw + row * kCfNB + col) = v;
     }
   }
   double sx = 0.0;
+  {
+    // t = Dinv rhs: first 16 columns from I11 (rows < 16) or Dinv21, the other 16 from I22 (rows >= 16);
+    // the zeros above the diagonals are stored, so both loops are uniform
+    const double* ra = lane < 16 ? B12 + lane * kCfLdD : B21 + (lane - 16) * kCfLdD;
+    const double* rb = B11 + (lane & 15) * kCfLdD;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 16; k += 2) {
+      const double2 a = *reinterpret_cast<const double2*>(ra + k), b = *reinterpret_cast<const double2*>(rb + k);
+      s0 = fma(a.x, red[k], s0);
+      s1 = fma(a.y, red[k + 1], s1);
+      s2 = fma(b.x, red[16 + k], s2);
+      s3 = fma(b.y, red[17 + k], s3);
+    }
+    sx = (s0 + s1) + (lane >= 16 ? s2 + s3 : 0.0);
+  }
   if (lane < nb) {
-    for (int k = 0; k <= lane; k++) sx = fma(Dn[lane * kCfLdD + k], red[k], sx);
     prm.tvec[(size_t)w * Mg + Jd + lane] = sx;
   }
   const double q2 = warp_sum(sx * sx);

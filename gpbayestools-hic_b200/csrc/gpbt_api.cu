@@ -1118,6 +1118,9 @@ int ensure_fused(gpbt_chain* ch, int64_t rows) {
 // (b) + (c) fused: lp[w] from z_var (kernel (a)) and mean, for walkers [0, N) of the chunk.  One launch
 // per 32-column panel; the walkers go through in sub-batches whose factors stay L2 resident
 // (option "chol_batch", default: what fits in ~60 % of the L2).
+// (Running kernel (a) per sub-batch on the sub-batch's stream, so that it overlaps another sub-batch's
+// Cholesky launches, was measured: no gain -- 3.47 vs 3.49 ms at N = 4096 -- and it makes the result depend
+// on the split through kernel (a)'s walker-tile width.  Kernel (a) runs once for the whole chunk.)
 int run_chol_fused(gpbt_chain* ch, double* lp, int* n_notpd, double notpd_value, int64_t N, cudaStream_t st) {
   CholFusedParams prm;
   prm.Fp = ch->cf_Fp; prm.Fd = ch->cf_Fd; prm.UT = ch->cf_UT; prm.z_var = ch->z_var; prm.mean = ch->cf_mean;

@@ -13,7 +13,7 @@ from . import _lib
 from .state import EmulatorState
 
 _COV_CHUNK_BYTES = 4 << 30  # device bytes of covariance produced per chunk by predict()
-_FANOUT_MIN_ROWS = 1024     # rows per GPU below which a further GPU does not pay (gpbt_fanout_*'s default)
+_FANOUT_MIN_ROWS = 256      # rows per GPU below which a further GPU does not pay (gpbt_fanout_*'s default)
 
 
 def _require_gpu():
@@ -321,7 +321,7 @@ class DeviceChain:
 
     def log_target(self, X, oob_value, path=None, max_devices=None):
         """Host buffers in/out: gpbt_log_posterior_host (H2D, kernels, D2H, one sync) on this chain's GPU,
-        or -- with `devices` and a batch of at least 2 x 1024 rows -- gpbt_fanout_log_posterior_host over
+        or -- with `devices` and a batch of at least 2 x 256 rows -- gpbt_fanout_log_posterior_host over
         several GPUs.  max_devices: None = automatic, 1 = this GPU only, n = use n GPUs whatever N is."""
         _require_gpu()
         X = as_rows(X, self.p)

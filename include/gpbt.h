@@ -259,7 +259,7 @@ int gpbt_host_temp_exchange(const double* lp_host, const double* temps_host, int
  * replica.  gpbt_fanout_log_posterior_host splits X_host [N,p] into contiguous row blocks, each worker
  * stages its block through pinned memory to its GPU, runs gpbt_log_posterior there and copies its lp
  * block into lp_host; the call returns when all blocks are back.  No collective is involved.
- * max_devices: 0 = automatic (one device per `fanout_min_rows` rows, default 1024, at most all),
+ * max_devices: 0 = automatic (one device per `fanout_min_rows` rows, default 256, at most all),
  * else the number of replicas to use.  *devices_used (may be NULL) reports how many took part.
  * The chains stay owned by the caller and must outlive the fan-out.                             */
 typedef struct gpbt_fanout* gpbt_fanout_t;

@@ -69,7 +69,7 @@ def test_emulator_predict(case):
         # (a 4-row call uses a narrower walker tile than the 256-row one: same values up to
         # summation order)
         m1 = emu.predict(Xin[:4], return_cov=False, extra_std=0)
-        assert rel_err(m1, mean0[:4]) <= 1e-12
+        assert rel_err(m1, mean0[:4]) <= (1e-12 if REL_G == REL else 1e-3 * REL_G)   # (ill-conditioned case: tests/helpers.py)
 
 
 def test_chain_predict_and_mvn(case):
@@ -132,7 +132,9 @@ def test_log_posterior(case, path):
     assert ch.last_notpd == 0
     # N = 1 and 1-D input (PTLMC's probe calls) equal the corresponding batch rows
     i = int(np.flatnonzero(fin)[0])
-    assert abs(ch.log_target(g["X"][i], -np.inf, path=path)[0] - lp[i]) <= 1e-10
+    # (another batch size = another walker tile = another summation order: 1e-10, or what the
+    # ill-conditioned case allows)
+    assert abs(ch.log_target(g["X"][i], -np.inf, path=path)[0] - lp[i]) <= (1e-10 if ABS_G == ABS_LP else 1e-2 * ABS_G)
     ch.release()
     # full (non-diagonal) experimental covariance, BASELINE config 4
     ch2 = DeviceChain(states, g["lo"], g["hi"], g["y_exp"].reshape(-1), goldens.cov_exp_sys(g))
