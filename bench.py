@@ -16,7 +16,8 @@ A "step" is one pass of the hot path (Chain.log_posterior) over one fresh batch 
   e2e       the same metric through the host API with HOST buffers (pinned): H2D of X, kernels,
             (all-gather), D2H of lp, one synchronisation per step -- wall clock
   sustained >= 2 s of back-to-back steps without flush: throughput, SM clock, power-cap flag
-  roofline, roofline_b, roofline_c   kernels (a), (b), (c) alone at 4096 walkers, CUDA events:
+  roofline, roofline_b, roofline_c, roofline_bc_fused   kernels (a), (b), (c) alone and (b)+(c) as fused on the
+            dense path, at 4096 walkers, CUDA events:
             algorithmic FP64 flops or HBM bytes / time vs the cuBLAS DGEMM rate measured in this run
             (MEASURED_PEAKS.json has no FP64 entry) and vs MEASURED_PEAKS.json's hbm_gbs
   dense_path  the named-kernel contract (a) -> (b) -> (c) at 4096 walkers
@@ -635,6 +636,20 @@ def single_gpu_records(args, torch, dev, chain, states, sts, g, Xh, Xd, lp_check
         "peak_source": peak_src, "ms_per_launch": kc_ms, "walkers_per_launch": N,
         "algorithmic_flops_per_eval": flops_cholesky(m), "algorithmic_bytes_per_eval": 8 * (m * m + m),
         "hbm_GBps_algorithmic": 8 * (m * m + m) * N / (kc_ms * 1e-3) / 1e9}
+    if dense is not None and dense["walkers"] == N:
+        # (b) + (c) as they run on the dense path: fused (the covariance is generated inside the Cholesky
+        # launches); their time = dense step - kernel (a) alone (the mean kernel, ~1 %, stays in)
+        fl_bc = 2 * q * m + q * m * (m + 1) + flops_cholesky(m)      # (b) lower triangle + (c)
+        bc_ms = dense["ms_per_step"] - ka_ms
+        ach_bc = fl_bc * N / (bc_ms * 1e-3) / 1e12
+        rec["roofline_bc_fused"] = {
+            "kernel": "chol_fused_panel_kernel + chol_fused_factor_kernel: kernels (b) + (c) fused, dense path",
+            "bound": "tensor", "achieved": ach_bc, "peak": peak, "unit": "TFLOP/s", "frac": ach_bc / peak, "traffic": None,
+            "peak_source": peak_src, "ms_per_launch": bc_ms, "walkers_per_launch": N,
+            "how": "dense-path step minus kernel (a) timed alone, both CUDA events in this run",
+            "algorithmic_flops_per_eval": fl_bc,
+            "note": "q m (m + 1) + 2 q m for the lower triangle of (b), m^3 / 3 + m^2 for (c); nothing of size N m^2 "
+                    "is written: the factor (lower blocks only, 332 KB per walker) is the only per-walker HBM traffic"}
     rec["dense_path"] = dense
     rec["configs"] = configs
 

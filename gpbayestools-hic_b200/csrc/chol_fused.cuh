@@ -42,6 +42,12 @@ struct CholFusedParams {
   const double* __restrict__ Fp;     // packed panels of F (layout of the factor), rows >= M and columns >= M zero
   const double* __restrict__ Fd;     // [nP][32][32] diagonal blocks of F, identity padded
   const double* __restrict__ UT;     // [Mg][Qp]  U^T, zero padded
+  // dense source (stand-alone mvn_loglike, chains with a no-PCA / exp-diag emulator): the covariances exist
+  // in memory, cov_src [N][M][M] row major (+ cov_add [M][M] or null); then Fp / Fd / UT / z_var are unused
+  // (Qp = 0) and the accumulators start from the tile of cov_src instead of the tile of F
+  const double* __restrict__ cov_src;
+  const double* __restrict__ cov_add;
+  int dense_vec;                     // dense source: rows are 16-byte aligned and M is even
   const double* __restrict__ z_var;  // [N][ldz]  v_w
   const double* __restrict__ mean;   // [N][M]
   const double* __restrict__ y_exp;  // [M]
@@ -61,6 +67,31 @@ struct CholFusedParams {
   int flags;                         // debugging: 1 = wait for the predecessor first thing
   long long* dbg;                    // null, or [16 launches][32 walkers][8 tiles][8] clock64 stamps (tuning)
 };
+
+// (C + cov_add)[r][c], [r][c + 1] of walker w from the dense source (c even); zero outside the matrix
+__device__ __forceinline__ double2 cf_dense_pair(const CholFusedParams& prm, int64_t w, int r, int c) {
+  const int M = prm.M;
+  double2 v = make_double2(0.0, 0.0);
+  if (r < M && c < M) {
+    const double* row = prm.cov_src + ((size_t)w * M + r) * M;
+    if (prm.dense_vec) {            // M even, 16-byte aligned bases: c + 1 < M as well
+      v = __ldcg(reinterpret_cast<const double2*>(row + c));
+      if (prm.cov_add != nullptr) {
+        const double2 a = ldg2(prm.cov_add + (size_t)r * M + c);
+        v.x += a.x;
+        v.y += a.y;
+      }
+    } else {
+      v.x = __ldcg(row + c);
+      if (c + 1 < M) v.y = __ldcg(row + c + 1);
+      if (prm.cov_add != nullptr) {
+        v.x += __ldg(prm.cov_add + (size_t)r * M + c);
+        if (c + 1 < M) v.y += __ldg(prm.cov_add + (size_t)r * M + c + 1);
+      }
+    }
+  }
+  return v;
+}
 
 __device__ __forceinline__ void cf_stamp(const CholFusedParams& prm, int J, int64_t w, int slot) {
   if (prm.dbg != nullptr && threadIdx.x == 0 && w < 32 && blockIdx.x < 8)
@@ -86,6 +117,8 @@ inline size_t chol_fused_smem_bytes(int Mg) {
 static_assert(kCfLdD == kSpLd, "tile16_mma works on kSpLd-strided tiles");
 static_assert(kCfRows * kCfLd <= kCfStages * kCfStageDoubles, "a regular tile parks its 64 rows over the ring");
 
+// DENSE: the covariances come from memory (prm.cov_src) instead of being generated from F and U
+template <bool DENSE>
 __global__ void __launch_bounds__(kCfThreads, 4) chol_fused_panel_kernel(const CholFusedParams prm, int J, int64_t w_first) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* ring = reinterpret_cast<double*>(smem_raw);                    // [stages][A | B]
@@ -127,7 +160,10 @@ __global__ void __launch_bounds__(kCfThreads, 4) chol_fused_panel_kernel(const C
 #pragma unroll
         for (int nbk = 0; nbk < 4; nbk++) {
           double2 v = make_double2(0.0, 0.0);
-          if (active) v = ldg2(Fpan + ((size_t)nbk * RkJ + rel0 + 16 * warp + 8 * mb + g) * 8 + 2 * t);
+          if (active) {
+            if (DENSE) v = cf_dense_pair(prm, w, r0 + 16 * warp + 8 * mb + g, J + 8 * nbk + 2 * t);
+            else v = ldg2(Fpan + ((size_t)nbk * RkJ + rel0 + 16 * warp + 8 * mb + g) * 8 + 2 * t);
+          }
           acc[mb][nbk][0] = v.x;
           acc[mb][nbk][1] = v.y;
         }
@@ -165,7 +201,7 @@ __global__ void __launch_bounds__(kCfThreads, 4) chol_fused_panel_kernel(const C
 #pragma unroll
     for (int s0 = 0; s0 < kCfStages - 1; s0++) issue(s0);
     // rank-Q term of the covariance tile: acc += (v U^T[rows]) U^T[cols]^T
-    if (active) {
+    if (!DENSE && active) {
       const double* zv = prm.z_var + w * prm.ldz;
       for (int k0 = 0; k0 < Qp; k0 += 4) {
         const double vk = (k0 + t < prm.Q) ? __ldcg(zv + k0 + t) : 0.0;
@@ -281,24 +317,31 @@ __global__ void __launch_bounds__(kCfThreads, 4) chol_fused_panel_kernel(const C
   const int Rv0 = min(kCfNB, Mg - Jd);            // rows that exist in the storage (16 or 32)
   const bool is_last = Jd + kCfNB >= M;
   const int RkJ = has_panel ? cf_panel_rows(Mg, K) : 0;
+  cf_stamp(prm, J, w, 0);
+  pdl_launch_dependents();
+  // the prologue launch follows kernels outside the chain (z_var, mean, skip, a dense source): it waits
+  // before it reads anything
+  if (!has_panel || (prm.flags & 1)) pdl_wait_prior_grids();
   double accp[4][2], accd[4][2];                  // warp: rows 8 warp .. 8 warp + 7, 32 columns each
   {
     const double* Fpan = prm.Fp + (has_panel ? cf_panel_off(Mg, K) : 0);
     const double* Fdb = prm.Fd + (size_t)(K + 1) * kCfNB * kCfNB;
 #pragma unroll
     for (int nbk = 0; nbk < 4; nbk++) {
-      double2 v = make_double2(0.0, 0.0);
-      if (has_panel && 8 * warp < Rv0) v = ldg2(Fpan + ((size_t)nbk * RkJ + 8 * warp + g) * 8 + 2 * t);
+      double2 v = make_double2(0.0, 0.0), d;
+      if (DENSE) {
+        if (has_panel) v = cf_dense_pair(prm, w, Jd + 8 * warp + g, J + 8 * nbk + 2 * t);
+        d = cf_dense_pair(prm, w, Jd + 8 * warp + g, Jd + 8 * nbk + 2 * t);   // (padding: identity, set below)
+      } else {
+        if (has_panel && 8 * warp < Rv0) v = ldg2(Fpan + ((size_t)nbk * RkJ + 8 * warp + g) * 8 + 2 * t);
+        d = ldg2(Fdb + (size_t)(8 * warp + g) * kCfNB + 8 * nbk + 2 * t);
+      }
       accp[nbk][0] = v.x;
       accp[nbk][1] = v.y;
-      const double2 d = ldg2(Fdb + (size_t)(8 * warp + g) * kCfNB + 8 * nbk + 2 * t);
       accd[nbk][0] = d.x;
       accd[nbk][1] = d.y;
     }
   }
-  cf_stamp(prm, J, w, 0);
-  pdl_launch_dependents();
-  if (!has_panel || (prm.flags & 1)) pdl_wait_prior_grids();   // the prologue launch follows kernels outside the chain (z_var, mean, skip)
   if (prm.skip != nullptr && __ldcg(prm.skip + w)) return;
   __syncthreads();
 
@@ -336,7 +379,7 @@ __global__ void __launch_bounds__(kCfThreads, 4) chol_fused_panel_kernel(const C
     yrow = __ldcg(prm.mean + w * M + Jd + rr);
     if (prm.y_exp) yrow -= prm.y_exp[Jd + rr];
   }
-  {
+  if (!DENSE) {
     // rank-Q term for both tiles
     const double* zv = prm.z_var + w * prm.ldz;
     const int row = min(Jd + 8 * warp + g, Mg - 1);

@@ -125,6 +125,21 @@ Options g_opt;
 long long* g_cf_dbg = nullptr;            // managed buffer of the fused Cholesky's timing stamps (option cf_debug)
 constexpr size_t kCfDbgBytes = 16 * 32 * 8 * 8 * sizeof(long long);
 constexpr int kCfMaxStreams = 4;
+// aux streams / events the fused Cholesky spreads its sub-batches over (see launch_chol_fused)
+struct FusedStreams {
+  cudaStream_t aux[kCfMaxStreams] = {nullptr, nullptr, nullptr, nullptr};   // [0] unused: the caller's stream
+  cudaEvent_t done[kCfMaxStreams] = {nullptr, nullptr, nullptr, nullptr}, fork = nullptr;
+  void destroy() {
+    for (int i = 0; i < kCfMaxStreams; i++) {
+      if (aux[i]) cudaStreamDestroy(aux[i]);
+      if (done[i]) cudaEventDestroy(done[i]);
+      aux[i] = nullptr; done[i] = nullptr;
+    }
+    if (fork) cudaEventDestroy(fork);
+    fork = nullptr;
+  }
+};
+
 
 int set_option_value(const char* key, const char* value) {
   const std::string k = key ? key : "";
@@ -236,8 +251,7 @@ struct gpbt_chain {
   double *cf_Fp = nullptr, *cf_Fd = nullptr, *cf_UT = nullptr;
   double *cf_L = nullptr, *cf_dinv = nullptr, *cf_draw = nullptr, *cf_tvec = nullptr, *cf_logdet = nullptr, *cf_tsq = nullptr, *cf_mean = nullptr;
   int* cf_bad = nullptr;
-  cudaStream_t cf_streams[4] = {nullptr, nullptr, nullptr, nullptr};   // [0] unused: the caller's stream
-  cudaEvent_t cf_done[4] = {nullptr, nullptr, nullptr, nullptr}, cf_fork = nullptr;
+  FusedStreams cf_fs;
   bool lr_separable = false;          // R is block diagonal over the emulators
   std::vector<double*> R_blocks;      // per-emulator q_e x q_e copies of the diagonal blocks of R
   double s_perp, logdetF_half;
@@ -624,6 +638,8 @@ int run_chol_stepped(const CholParams& prm, cudaStream_t st) {
   return 0;
 }
 
+int run_chol_fused_dense(const CholParams& cp, cudaStream_t st);   // (defined with the fused launcher below)
+
 int run_chol(const double* mean, const double* y_exp, double* cov, const double* cov_add, double* lp,
              int* n_notpd, const unsigned char* skip, double notpd_value, double add_const, int64_t N, int m,
              cudaStream_t st) {
@@ -639,7 +655,7 @@ int run_chol(const double* mean, const double* y_exp, double* cov, const double*
   const size_t wsmem = chol_warp_smem_bytes(m);
   bool use_warp = m <= 80;
   if (which == 'w') use_warp = true;
-  if (which == 'c' || which == 's' || which == 'b') use_warp = false;
+  if (which == 'c' || which == 's' || which == 'b' || which == 'f') use_warp = false;
   if (use_warp && wsmem <= (size_t)max_optin_smem()) {
     if (int r = ensure_dynamic_smem<chol_warp_kernel>(wsmem)) return r;
     chol_warp_kernel<<<(unsigned)N, 32, wsmem, st>>>(prm);
@@ -650,8 +666,12 @@ int run_chol(const double* mean, const double* y_exp, double* cov, const double*
   // per-walker kernels once there are enough walkers to fill the machine per launch (measured at
   // m = 300: 0.92 vs 0.96 ms at N = 512, 9.4 vs 11.2 ms at N = 8192); below that its 19 dependent
   // launches cost more than one latency-bound kernel.  GPBT_CHOL=batch / staged / cta force a variant.
+  // batches: the fused kernels (chol_fused.cuh) with the covariances as a dense source -- packed factor in
+  // a work buffer (cov is left untouched), one launch per 32-column panel + a factor kernel; before them
+  // the stepped kernels (two launches per panel, in place), still selectable
+  if (which ? which == 'f' : N >= 256) return run_chol_fused_dense(prm, st);
   const bool aligned_rows = (m % 2 == 0) && ((reinterpret_cast<uintptr_t>(cov) & 15) == 0);
-  const bool want_stepped = which ? which == 'b' : N >= 256;
+  const bool want_stepped = which ? which == 'b' : false;
   if (aligned_rows && want_stepped) return run_chol_stepped(prm, st);
   // staged kernel (operand stream through a cp.async ring): needs 16-byte aligned rows and its
   // fixed block assignment covers m <= 352
@@ -992,16 +1012,14 @@ int chain_build(gpbt_chain* ch, const gpbt_emulator_t* emus, int n_emu, int p, c
 
 namespace {
 void release_stepped_buffer(int device, cudaStream_t st);   // defined next to run_chol_stepped
+void release_fused_dense(int device, cudaStream_t st);      // defined next to run_chol_fused_dense
 }
 
 extern "C" int gpbt_chain_destroy(gpbt_chain_t ch) {
   if (!ch) return 0;
   if (ch->stream) release_stepped_buffer(ch->device, ch->stream);
-  for (int i = 0; i < 4; i++) {
-    if (ch->cf_streams[i]) cudaStreamDestroy(ch->cf_streams[i]);
-    if (ch->cf_done[i]) cudaEventDestroy(ch->cf_done[i]);
-  }
-  if (ch->cf_fork) cudaEventDestroy(ch->cf_fork);
+  if (ch->stream) release_fused_dense(ch->device, ch->stream);
+  ch->cf_fs.destroy();
   for (double* d : ch->R_blocks) cudaFree(d);
   for (double* d : ch->base_like) cudaFree(d);
   if (ch->zc_x_host) cudaFreeHost(ch->zc_x_host);
@@ -1118,29 +1136,26 @@ int ensure_fused(gpbt_chain* ch, int64_t rows) {
 // (b) + (c) fused: lp[w] from z_var (kernel (a)) and mean, for walkers [0, N) of the chunk.  One launch
 // per 32-column panel; the walkers go through in sub-batches whose factors stay L2 resident
 // (option "chol_batch", default: what fits in ~60 % of the L2).
-// (Running kernel (a) per sub-batch on the sub-batch's stream, so that it overlaps another sub-batch's
-// Cholesky launches, was measured: no gain -- 3.47 vs 3.49 ms at N = 4096 -- and it makes the result depend
-// on the split through kernel (a)'s walker-tile width.  Kernel (a) runs once for the whole chunk.)
-int run_chol_fused(gpbt_chain* ch, double* lp, int* n_notpd, double notpd_value, int64_t N, cudaStream_t st) {
-  CholFusedParams prm;
-  prm.Fp = ch->cf_Fp; prm.Fd = ch->cf_Fd; prm.UT = ch->cf_UT; prm.z_var = ch->z_var; prm.mean = ch->cf_mean;
-  prm.y_exp = ch->y_exp; prm.skip = ch->skip; prm.L = ch->cf_L; prm.dinv = ch->cf_dinv; prm.draw = ch->cf_draw; prm.tvec = ch->cf_tvec;
-  prm.logdet = ch->cf_logdet; prm.tsq = ch->cf_tsq; prm.bad = ch->cf_bad; prm.lp = lp; prm.n_notpd = n_notpd;
-  prm.notpd_value = notpd_value; prm.add_const = kSysConst; prm.N = N; prm.Lstride = ch->Lstride; prm.ldz = ch->Q;
-  prm.M = ch->M; prm.Mg = ch->Mg; prm.Q = ch->Q; prm.Qp = ch->Qp;
+// Launches of the fused Cholesky over walkers [0, N): sub-batches round-robin over up to kCfMaxStreams
+// streams (the caller's + aux[1..]): while one sub-batch is in its factor kernel or in the tail of a panel
+// launch, the DMMA work of another fills the machine.  Options "chol_streams" / "chol_batch" override the
+// defaults.  prm carries everything but the debugging fields.
+int launch_chol_fused(CholFusedParams prm, int64_t N, FusedStreams* fs, cudaStream_t st) {
   prm.dbg = nullptr;
   prm.flags = g_opt.cf_debug.load() >> 4;      // (cf_debug = 16 * flags + record-stamps bit)
   if (g_opt.cf_debug.load() & 1) {
     if (!g_cf_dbg) CU(cudaMallocManaged(&g_cf_dbg, kCfDbgBytes));
     prm.dbg = g_cf_dbg;
   }
-  const size_t smem = chol_fused_smem_bytes(ch->Mg);
-  if (smem > (size_t)max_optin_smem()) return fail(GPBT_ESHAPE, "fused Cholesky: M = %d observables do not fit", ch->M);
-  if (int r = ensure_dynamic_smem<chol_fused_panel_kernel>(smem)) return r;
+  const int Mg = prm.Mg;
+  const size_t smem = chol_fused_smem_bytes(Mg);
+  if (smem > (size_t)max_optin_smem()) return fail(GPBT_ESHAPE, "fused Cholesky: M = %d observables do not fit", prm.M);
+  const bool dense = prm.cov_src != nullptr;
+  if (int r = dense ? ensure_dynamic_smem<chol_fused_panel_kernel<true>>(smem)
+                    : ensure_dynamic_smem<chol_fused_panel_kernel<false>>(smem))
+    return r;
   if (int r = ensure_dynamic_smem<chol_fused_factor_kernel>(kCfFactorSmem)) return r;
-  // Sub-batches go round-robin over up to kCfMaxStreams streams (the caller's + the chain's own): while one
-  // sub-batch is in its factor kernel or in the tail of a panel launch, the DMMA work of another fills
-  // the machine.  Options "chol_streams" / "chol_batch" override the defaults.
+  void (*panel)(CholFusedParams, int, int64_t) = dense ? chol_fused_panel_kernel<true> : chol_fused_panel_kernel<false>;
   int n_streams = (int)g_opt.chol_streams.load();
   if (n_streams <= 0) n_streams = N >= 2048 ? 2 : 1;
   n_streams = std::min(n_streams, kCfMaxStreams);
@@ -1151,29 +1166,28 @@ int run_chol_fused(gpbt_chain* ch, double* lp, int* n_notpd, double notpd_value,
   n_streams = (int)std::min<int64_t>(n_streams, n_batches);
   if (n_streams > 1) {
     for (int i = 1; i < n_streams; i++)
-      if (!ch->cf_streams[i]) {
-        CU(cudaStreamCreateWithFlags(&ch->cf_streams[i], cudaStreamNonBlocking));
-        CU(cudaEventCreateWithFlags(&ch->cf_done[i], cudaEventDisableTiming));
+      if (!fs->aux[i]) {
+        CU(cudaStreamCreateWithFlags(&fs->aux[i], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&fs->done[i], cudaEventDisableTiming));
       }
-    if (!ch->cf_fork) CU(cudaEventCreateWithFlags(&ch->cf_fork, cudaEventDisableTiming));
-    CU(cudaEventRecord(ch->cf_fork, st));
-    for (int i = 1; i < n_streams; i++) CU(cudaStreamWaitEvent(ch->cf_streams[i], ch->cf_fork, 0));
+    if (!fs->fork) CU(cudaEventCreateWithFlags(&fs->fork, cudaEventDisableTiming));
+    CU(cudaEventRecord(fs->fork, st));
+    for (int i = 1; i < n_streams; i++) CU(cudaStreamWaitEvent(fs->aux[i], fs->fork, 0));
   }
-  const int Mg = ch->Mg;
   for (int64_t b = 0; b < n_batches; b++) {
     const int64_t w0 = b * batch, nw = std::min(batch, N - w0);
-    cudaStream_t sb = (b % n_streams == 0) ? st : ch->cf_streams[b % n_streams];
+    cudaStream_t sb = (b % n_streams == 0) ? st : fs->aux[b % n_streams];
     for (int J = -kCfNB; J + kCfNB < Mg; J += kCfNB) {
       const int tiles = (J >= 0 && Mg > J + 2 * kCfNB) ? (Mg - J - 2 * kCfNB + kCfRows - 1) / kCfRows : 0;
       if (prm.flags & 4) {   // plain stream order, no programmatic launch
-        chol_fused_panel_kernel<<<dim3((unsigned)(1 + tiles), (unsigned)nw), kCfThreads, smem, sb>>>(prm, J, w0);
+        panel<<<dim3((unsigned)(1 + tiles), (unsigned)nw), kCfThreads, smem, sb>>>(prm, J, w0);
         LAUNCH_CHECK();
         chol_fused_factor_kernel<<<dim3((unsigned)((nw + kCfFactorWarps - 1) / kCfFactorWarps)), kCfFactorWarps * 32,
                                    kCfFactorSmem, sb>>>(prm, J + kCfNB, w0, nw);
         LAUNCH_CHECK();
         continue;
       }
-      CU(launch_pdl(chol_fused_panel_kernel, dim3((unsigned)(1 + tiles), (unsigned)nw), kCfThreads, smem, sb, prm, J, w0));
+      CU(launch_pdl(panel, dim3((unsigned)(1 + tiles), (unsigned)nw), kCfThreads, smem, sb, prm, J, w0));
       LAUNCH_CHECK();
       CU(launch_pdl(chol_fused_factor_kernel, dim3((unsigned)((nw + kCfFactorWarps - 1) / kCfFactorWarps)),
                     kCfFactorWarps * 32, kCfFactorSmem, sb, prm, J + kCfNB, w0, nw));
@@ -1181,10 +1195,77 @@ int run_chol_fused(gpbt_chain* ch, double* lp, int* n_notpd, double notpd_value,
     }
   }
   for (int i = 1; i < n_streams; i++) {
-    CU(cudaEventRecord(ch->cf_done[i], ch->cf_streams[i]));
-    CU(cudaStreamWaitEvent(st, ch->cf_done[i], 0));
+    CU(cudaEventRecord(fs->done[i], fs->aux[i]));
+    CU(cudaStreamWaitEvent(st, fs->done[i], 0));
   }
   return 0;
+}
+
+// (Running kernel (a) per sub-batch on the sub-batch's stream, so that it overlaps another sub-batch's
+// Cholesky launches, was measured: no gain -- 3.47 vs 3.49 ms at N = 4096 -- and it makes the result depend
+// on the split through kernel (a)'s walker-tile width.  Kernel (a) runs once for the whole chunk.)
+int run_chol_fused(gpbt_chain* ch, double* lp, int* n_notpd, double notpd_value, int64_t N, cudaStream_t st) {
+  CholFusedParams prm;
+  prm.Fp = ch->cf_Fp; prm.Fd = ch->cf_Fd; prm.UT = ch->cf_UT; prm.cov_src = nullptr; prm.cov_add = nullptr; prm.dense_vec = 0;
+  prm.z_var = ch->z_var; prm.mean = ch->cf_mean;
+  prm.y_exp = ch->y_exp; prm.skip = ch->skip; prm.L = ch->cf_L; prm.dinv = ch->cf_dinv; prm.draw = ch->cf_draw; prm.tvec = ch->cf_tvec;
+  prm.logdet = ch->cf_logdet; prm.tsq = ch->cf_tsq; prm.bad = ch->cf_bad; prm.lp = lp; prm.n_notpd = n_notpd;
+  prm.notpd_value = notpd_value; prm.add_const = kSysConst; prm.N = N; prm.Lstride = ch->Lstride; prm.ldz = ch->Q;
+  prm.M = ch->M; prm.Mg = ch->Mg; prm.Q = ch->Q; prm.Qp = ch->Qp;
+  return launch_chol_fused(prm, N, &ch->cf_fs, st);
+}
+
+// Stand-alone batched mvn_loglike on materialised covariances through the same kernels (dense source).
+// Work buffers and streams: one grow-only set per (device, stream).
+struct FusedDenseCache {
+  double* buf = nullptr;
+  size_t bytes = 0;
+  FusedStreams fs;
+};
+std::map<std::pair<int, cudaStream_t>, FusedDenseCache> g_fused_dense;
+std::mutex g_fused_dense_mutex;
+
+int run_chol_fused_dense(const CholParams& cp, cudaStream_t st) {
+  const int M = cp.m, Mg = (int)round_up(M, 16);
+  const int64_t N = cp.N, Lstride = std::max<int64_t>(cf_factor_doubles(M), 1);
+  const size_t per_row = (size_t)(Lstride + 2 * kCfNB * kCfNB + Mg + 2) * sizeof(double) + sizeof(int);
+  FusedDenseCache* c;
+  {
+    std::lock_guard<std::mutex> lock(g_fused_dense_mutex);
+    c = &g_fused_dense[std::make_pair(current_device(), st)];
+    if ((size_t)N * per_row > c->bytes) {
+      if (c->buf) cudaFree(c->buf);
+      c->buf = nullptr;
+      c->bytes = 0;
+      CU(cudaMalloc(&c->buf, (size_t)N * per_row));
+      c->bytes = (size_t)N * per_row;
+      g_ws_generation++;
+    }
+  }
+  CholFusedParams prm;
+  prm.Fp = prm.Fd = prm.UT = prm.z_var = nullptr;
+  prm.dense_vec = (M % 2 == 0) && ((reinterpret_cast<uintptr_t>(cp.cov) & 15) == 0) &&
+                  (cp.cov_add == nullptr || (reinterpret_cast<uintptr_t>(cp.cov_add) & 15) == 0);
+  prm.cov_src = cp.cov; prm.cov_add = cp.cov_add; prm.mean = cp.mean; prm.y_exp = cp.y_exp; prm.skip = cp.skip;
+  prm.L = c->buf;
+  prm.dinv = prm.L + (size_t)N * Lstride;
+  prm.draw = prm.dinv + (size_t)N * kCfNB * kCfNB;
+  prm.tvec = prm.draw + (size_t)N * kCfNB * kCfNB;
+  prm.logdet = prm.tvec + (size_t)N * Mg;
+  prm.tsq = prm.logdet + N;
+  prm.bad = reinterpret_cast<int*>(prm.tsq + N);
+  prm.lp = cp.lp; prm.n_notpd = cp.n_notpd; prm.notpd_value = cp.notpd_value; prm.add_const = cp.add_const;
+  prm.N = N; prm.Lstride = Lstride; prm.ldz = 0; prm.M = M; prm.Mg = Mg; prm.Q = 0; prm.Qp = 0;
+  return launch_chol_fused(prm, N, &c->fs, st);
+}
+
+void release_fused_dense(int device, cudaStream_t st) {
+  std::lock_guard<std::mutex> lock(g_fused_dense_mutex);
+  auto it = g_fused_dense.find(std::make_pair(device, st));
+  if (it == g_fused_dense.end()) return;
+  if (it->second.buf) cudaFree(it->second.buf);
+  it->second.fs.destroy();
+  g_fused_dense.erase(it);
 }
 
 // Chain._predict into (mean, cov) for rows [0, N) of X; cov may be null

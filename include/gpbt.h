@@ -134,8 +134,9 @@ int gpbt_backtransform_diag(gpbt_emulator_t emu, const double* z_mean_dev, const
  * and cov + expdata_cov (src/mcmc.py:288-290):
  *   lp[i] = -1/2 y_i^T C_i^-1 y_i - sum(log(diag(chol(C_i)))),   y_i = mean_i - y_exp (y_exp may
  *   be NULL), C_i = cov_i + cov_add (cov_add may be NULL).
- * cov_dev [N,m,m] is OVERWRITTEN (its lower triangle receives the Cholesky factor, as dpotrf
- * does to its own copy).  Walkers whose matrix is not positive definite get lp = notpd_value and
+ * cov_dev [N,m,m] MAY BE OVERWRITTEN (the in-place kernels leave the Cholesky factor in its lower
+ * triangle, as dpotrf does to its own copy; batches of 256+ matrices go through the fused kernels, which
+ * keep their packed factor in a work buffer and leave cov_dev untouched).  Walkers whose matrix is not positive definite get lp = notpd_value and
  * increment *n_notpd_dev (may be NULL); the reference's own check is broken (both branches test
  * info < 0, src/mcmc.py:44-54) and would return garbage there.                               */
 int gpbt_mvn_loglike(const double* mean_dev, const double* y_exp_dev, double* cov_dev,

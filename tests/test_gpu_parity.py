@@ -531,10 +531,10 @@ def test_random_shapes_vs_oracle(shape):
 
 @pytest.mark.parametrize("m", [96, 130, 300, 602])
 def test_cholesky_variants_agree(m):
-    """gpbt_mvn_loglike through each Cholesky kernel that takes this size (staged default, register-fed
-    CTA kernel, warp-per-walker, and the opt-in stepped variant that advances all walkers panel by
-    panel) against scipy's dpotrf/dpotrs on random SPD matrices, with and without cov_add, plus a
-    non-positive-definite matrix."""
+    """gpbt_mvn_loglike through each Cholesky kernel that takes this size (staged, register-fed CTA kernel,
+    warp-per-walker, the stepped variant that advances all walkers panel by panel in place, and the fused
+    kernels with the covariances as a dense source -- the default for batches of 256+) against scipy's
+    dpotrf/dpotrs on random SPD matrices, with and without cov_add, plus a non-positive-definite matrix."""
     from gpbt_b200.device import mvn_loglike_batch
     rng = np.random.default_rng(m)
     N = 37
@@ -548,7 +548,7 @@ def test_cholesky_variants_agree(m):
     bad[5] -= 3.0 * np.eye(m)
     from gpbt_b200 import _lib
     try:
-        for which in ("", "cta", "warp", "batch"):
+        for which in ("", "cta", "warp", "batch", "fused"):
             _lib.set_option("chol", which or None)
             got = mvn_loglike_batch(dY, cov)
             assert np.max(np.abs(got - want)) <= ABS_LP, which
