@@ -264,6 +264,11 @@ struct gpbt_chain {
   unsigned char* skip = nullptr;
   int* notpd_dev = nullptr;
   cudaStream_t stream = nullptr;
+  // The workspaces below are shared by every call on this chain.  Calls may come in on different streams (the
+  // chain's own for the host API and the sampler, the caller's for the device API): when the stream changes,
+  // the previous one is drained first, so two calls never use the buffers at the same time.
+  cudaStream_t last_stream = nullptr;
+  bool last_stream_valid = false;
   int64_t ws_bytes = 0;
   // small-batch path: pinned host buffers mapped into the device address space (zero copy)
   double *zc_x_host = nullptr, *zc_x_dev = nullptr;      // [kZeroCopyRows, p]
@@ -1038,6 +1043,14 @@ extern "C" int64_t gpbt_chain_workspace_bytes(gpbt_chain_t ch) { return ch ? ch-
 
 namespace {
 
+// see gpbt_chain::last_stream
+int chain_enter_stream(gpbt_chain* ch, cudaStream_t st) {
+  if (ch->last_stream_valid && ch->last_stream != st) CU(cudaStreamSynchronize(ch->last_stream));
+  ch->last_stream = st;
+  ch->last_stream_valid = true;
+  return 0;
+}
+
 // rows of PC-space workspace (z_mean, z_var, extra, skip): grows to the largest N seen
 int ensure_rows(gpbt_chain* ch, int64_t N) {
   if (N <= ch->cap_rows) return 0;
@@ -1294,6 +1307,7 @@ int chain_predict_rows(gpbt_chain* ch, const double* X, double extra_scale, doub
 extern "C" int gpbt_chain_predict(gpbt_chain_t ch, const double* X, double extra_std_scale, double* mean,
                                   double* cov, int64_t N, void* stream) {
   if (!ch || !X || !mean || N < 0) return fail(GPBT_EINVAL, "gpbt_chain_predict: bad argument");
+  if (int r = chain_enter_stream(ch, (cudaStream_t)stream)) return r;
   const int64_t step = 32768;
   for (int64_t s = 0; s < N; s += step) {
     const int64_t nn = std::min(step, N - s);
@@ -1341,6 +1355,7 @@ int log_posterior_impl(gpbt_chain_t ch, const double* X, double oob_value, doubl
     return fail(GPBT_EINVAL, "chain lives on device %d, current device is %d", ch->device, current_device());
   if (N == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  if (int r = chain_enter_stream(ch, st)) return r;
   if (path == GPBT_PATH_AUTO)
     path = ch->has_lowrank ? GPBT_PATH_LOWRANK : (ch->has_diag ? GPBT_PATH_DIAG : GPBT_PATH_DENSE);
   if (path == GPBT_PATH_DIAG && !ch->has_diag)
