@@ -200,8 +200,42 @@ __global__ void __launch_bounds__(kCfThreads, 4) chol_fused_panel_kernel(const C
     };
 #pragma unroll
     for (int s0 = 0; s0 < kCfStages - 1; s0++) issue(s0);
-    // rank-Q term of the covariance tile: acc += (v U^T[rows]) U^T[cols]^T
-    if (!DENSE && active) {
+    // rank-Q term of the covariance tile: acc += (v U^T[rows]) U^T[cols]^T.  The rows of U^T this tile needs
+    // (64 on the A side, 32 on the B side) come into shared memory with one round of cp.async -- the third
+    // ring slot and the Dinv buffer are free until the operand stream / the epilogue need them -- instead of
+    // Q/4 rounds of dependent L2 loads per warp (which were most of a CTA's life in the first panels).
+    const bool stage_u = !DENSE && 64 * Qp <= kCfStageDoubles && 32 * Qp <= kCfNB * kCfLd;
+    if (stage_u) {
+      double* UA = ring + 2 * kCfStageDoubles;     // [64][Qp]
+      double* UB = Dv;                             // [32][Qp]
+      const double* srcA = prm.UT + (size_t)r0 * Qp;
+      const double* srcB = prm.UT + (size_t)J * Qp;
+      for (int idx = tid; idx < Rv * Qp / 2; idx += kCfThreads) cp_async16(UA + 2 * idx, srcA + 2 * idx);
+      for (int idx = tid; idx < kCfNB * Qp / 2; idx += kCfThreads) cp_async16(UB + 2 * idx, srcB + 2 * idx);
+      cp_async_commit();
+      double vk[6];
+      const double* zv = prm.z_var + w * prm.ldz;
+#pragma unroll
+      for (int s6 = 0; s6 < 6; s6++) vk[s6] = (4 * s6 + t < prm.Q) ? __ldcg(zv + 4 * s6 + t) : 0.0;
+      cp_async_wait<0>();
+      __syncthreads();
+      if (active) {
+#pragma unroll
+        for (int s6 = 0; s6 < 6; s6++)
+          if (4 * s6 < Qp) {
+            const int k = 4 * s6 + t;
+            double a[2], b[4];
+#pragma unroll
+            for (int mb = 0; mb < 2; mb++) a[mb] = vk[s6] * UA[(16 * warp + 8 * mb + g) * Qp + k];
+#pragma unroll
+            for (int nbk = 0; nbk < 4; nbk++) b[nbk] = UB[(8 * nbk + g) * Qp + k];
+#pragma unroll
+            for (int mb = 0; mb < 2; mb++)
+#pragma unroll
+              for (int nbk = 0; nbk < 4; nbk++) dmma884(acc[mb][nbk][0], acc[mb][nbk][1], a[mb], b[nbk]);
+          }
+      }
+    } else if (!DENSE && active) {
       const double* zv = prm.z_var + w * prm.ldz;
       for (int k0 = 0; k0 < Qp; k0 += 4) {
         const double vk = (k0 + t < prm.Q) ? __ldcg(zv + k0 + t) : 0.0;
@@ -258,6 +292,7 @@ __global__ void __launch_bounds__(kCfThreads, 4) chol_fused_panel_kernel(const C
     }
     cf_stamp(prm, J, w, 1);
     pdl_wait_prior_grids();          // Dinv_J is final
+    __syncthreads();     // every warp has left the rank-Q term and the operand stream: Dv and the ring are free
     {
       const double* dw = prm.dinv + (size_t)w * kCfNB * kCfNB;
       for (int idx = tid; idx < kCfNB * 16; idx += kCfThreads) {
@@ -266,8 +301,7 @@ __global__ void __launch_bounds__(kCfThreads, 4) chol_fused_panel_kernel(const C
       }
       cp_async_commit();
     }
-    __syncthreads();     // every warp has left the operand stream: the ring is free
-    // park the tile over it, rows <- rows Dinv^T (Dinv lower triangular: k blocks kk <= nbk only)
+    // park the tile over the ring, rows <- rows Dinv^T (Dinv lower triangular: k blocks kk <= nbk only)
     double* T = ring;
     if (active) {
 #pragma unroll
@@ -379,7 +413,38 @@ __global__ void __launch_bounds__(kCfThreads, 4) chol_fused_panel_kernel(const C
     yrow = __ldcg(prm.mean + w * M + Jd + rr);
     if (prm.y_exp) yrow -= prm.y_exp[Jd + rr];
   }
-  if (!DENSE) {
+  const bool stage_u0 = !DENSE && 64 * Qp <= kCfStageDoubles;
+  if (stage_u0) {
+    // rank-Q term for both tiles, U^T rows through shared memory (see the regular tile): [32][Qp] rows Jd..
+    // (A side and the diagonal block's B side), [32][Qp] rows J.. (the panel's B side)
+    double* UA = ring + 2 * kCfStageDoubles;
+    double* UB = UA + kCfNB * Qp;
+    const double* srcA = prm.UT + (size_t)Jd * Qp;
+    for (int idx = tid; idx < Rv0 * Qp / 2; idx += kCfThreads) cp_async16(UA + 2 * idx, srcA + 2 * idx);
+    for (int idx = Rv0 * Qp + tid; idx < kCfNB * Qp; idx += kCfThreads) UA[idx] = 0.0;
+    if (has_panel) {
+      const double* srcB = prm.UT + (size_t)J * Qp;
+      for (int idx = tid; idx < kCfNB * Qp / 2; idx += kCfThreads) cp_async16(UB + 2 * idx, srcB + 2 * idx);
+    }
+    cp_async_commit();
+    double vk[6];
+    const double* zv = prm.z_var + w * prm.ldz;
+#pragma unroll
+    for (int s6 = 0; s6 < 6; s6++) vk[s6] = (4 * s6 + t < prm.Q) ? __ldcg(zv + 4 * s6 + t) : 0.0;
+    cp_async_wait<0>();
+    __syncthreads();
+#pragma unroll
+    for (int s6 = 0; s6 < 6; s6++)
+      if (4 * s6 < Qp) {
+        const int k = 4 * s6 + t;
+        const double a = vk[s6] * UA[(8 * warp + g) * Qp + k];
+#pragma unroll
+        for (int nbk = 0; nbk < 4; nbk++) {
+          if (has_panel) dmma884(accp[nbk][0], accp[nbk][1], a, UB[(8 * nbk + g) * Qp + k]);
+          if (nbk <= warp) dmma884(accd[nbk][0], accd[nbk][1], a, UA[(8 * nbk + g) * Qp + k]);
+        }
+      }
+  } else if (!DENSE) {
     // rank-Q term for both tiles
     const double* zv = prm.z_var + w * prm.ldz;
     const int row = min(Jd + 8 * warp + g, Mg - 1);
