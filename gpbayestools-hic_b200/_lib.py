@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgpbt_b200.so")
+# (GPBT_B200_LIB: another build of the same library, e.g. a tuning variant; read once, at import)
+LIB_PATH = os.environ.get("GPBT_B200_LIB") or os.path.join(_HERE, "libgpbt_b200.so")
 
 KERNEL_RBF, KERNEL_MATERN32, KERNEL_PCGP = 0, 1, 2
 FLAG_NO_PCA, FLAG_EXP_DIAG = 1, 2

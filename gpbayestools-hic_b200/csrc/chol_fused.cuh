@@ -28,6 +28,7 @@ namespace gpbt {
 
 constexpr int kCfNB = 32;        // panel width
 constexpr int kCfThreads = 128;
+constexpr int kCfCtasPerSm = 4;  // by registers (128) and shared memory (54 KB)
 constexpr int kCfRows = 64;      // rows of a regular tile (16 per warp)
 constexpr int kCfStages = 3;     // ring depth, 16 columns per stage
 constexpr int kCfLd = kSpLd;     // row stride of 32-column tiles in shared memory
@@ -64,7 +65,8 @@ struct CholFusedParams {
   double notpd_value, add_const;
   int64_t N, Lstride, ldz;
   int M, Mg, Q, Qp;
-  int flags;                         // debugging: 1 = wait for the predecessor first thing
+  int early_after;                   // CTAs (in launch order) from this one on wait for the predecessor FIRST (see the kernel)
+  int flags;                         // debugging: 1 = every CTA waits for the predecessor first thing, 32 = none does
   long long* dbg;                    // null, or [16 launches][32 walkers][8 tiles][8] clock64 stamps (tuning)
 };
 
@@ -110,20 +112,22 @@ __host__ __device__ inline int64_t cf_factor_doubles(int M) {
 }
 
 constexpr int kCfStageDoubles = 2 * (kCfRows + kCfNB) * 8;   // A: [2][64][8], B: [2][32][8]
+constexpr int kCfUbDoubles = kCfNB * 24;   // the panel's own rows of U^T (Qp <= 24), staged for the rank-Q term
 inline size_t chol_fused_smem_bytes(int Mg) {
-  // ring + Dinv of the current panel + t[:J+32] + the right-hand side of the t solve
-  return sizeof(double) * ((size_t)kCfStages * kCfStageDoubles + (size_t)kCfNB * kCfLd + (size_t)Mg);
+  // ring + Dinv of the current panel + t[:J+32] + U^T[J:J+32]
+  return sizeof(double) * ((size_t)kCfStages * kCfStageDoubles + (size_t)kCfNB * kCfLd + (size_t)Mg + kCfUbDoubles);
 }
 static_assert(kCfLdD == kSpLd, "tile16_mma works on kSpLd-strided tiles");
 static_assert(kCfRows * kCfLd <= kCfStages * kCfStageDoubles, "a regular tile parks its 64 rows over the ring");
 
 // DENSE: the covariances come from memory (prm.cov_src) instead of being generated from F and U
 template <bool DENSE>
-__global__ void __launch_bounds__(kCfThreads, 4) chol_fused_panel_kernel(const CholFusedParams prm, int J, int64_t w_first) {
+__global__ void __launch_bounds__(kCfThreads, kCfCtasPerSm) chol_fused_panel_kernel(const CholFusedParams prm, int J, int64_t w_first) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* ring = reinterpret_cast<double*>(smem_raw);                    // [stages][A | B]
   double* Dv = ring + (size_t)kCfStages * kCfStageDoubles;               // [32][kCfLd] Dinv of panel J
   double* tvs = Dv + kCfNB * kCfLd;                                      // [J + 32] t so far
+  double* Ubuf = tvs + prm.Mg;                                           // [32][Qp] U^T rows J .. J + 31
   __shared__ uint64_t full_bar[kCfStages], empty_bar[kCfStages];
 
   const int M = prm.M, Mg = prm.Mg, Qp = prm.Qp;
@@ -133,6 +137,21 @@ __global__ void __launch_bounds__(kCfThreads, 4) chol_fused_panel_kernel(const C
   const int K = J / kCfNB;                      // panel index (J = -32: prologue, K = -1)
   const bool tile0 = blockIdx.x == 0;
   const bool has_panel = J >= 0;
+  // The predecessor (the factor kernel of this panel's diagonal block) writes Dinv_J and t[J:J+32]; the wait
+  // for it sits in front of their first use, BEHIND the operand stream -- for the CTAs that can be resident
+  // while it still runs.  A CTA that starts later got its slot from one of those, which had to pass its own
+  // wait first: for it the wait returns at once, so it waits first thing and fetches Dinv_J together with
+  // everything else instead of in a dependent round trip before the epilogue.
+  const bool early = has_panel && ((prm.flags & 1) || (!(prm.flags & 32) &&
+                     (int64_t)blockIdx.y * gridDim.x + blockIdx.x >= prm.early_after));
+  auto fetch_dinv = [&]() {
+    const double* dw = prm.dinv + (size_t)w * kCfNB * kCfNB;
+    for (int idx = tid; idx < kCfNB * 16; idx += kCfThreads) {
+      const int r = idx >> 4, c2 = idx & 15;
+      cp_async16(Dv + r * kCfLd + 2 * c2, dw + r * kCfNB + 2 * c2);
+    }
+    cp_async_commit();
+  };
   const int nst = has_panel ? J / 16 : 0;       // 16-column stages of the operand stream
   double* Lw = prm.L + (size_t)w * prm.Lstride;
 
@@ -173,10 +192,12 @@ __global__ void __launch_bounds__(kCfThreads, 4) chol_fused_panel_kernel(const C
     // No wait yet.  The predecessor is the factor kernel of this panel's diagonal block; it triggers this
     // launch only after ITS wait, i.e. once the previous panel launch has completed -- so the factor
     // panels < J, z_var and skip are final.  Only Dinv_J (and t[J:J+32] in tile 0) are still being written:
-    // the wait sits in front of their first use, and the operand stream overlaps the factor kernel.
-    if (prm.flags & 1) pdl_wait_prior_grids();
+    // the wait sits in front of their first use, and the operand stream overlaps the factor kernel
+    // (`early`: see the top).
+    if (early) pdl_wait_prior_grids();
     if (prm.skip != nullptr && __ldcg(prm.skip + w)) return;
     __syncthreads();   // barriers initialised
+    if (early) fetch_dinv();
 
     // operand stage s = columns 16 s .. 16 s + 15 = sub-blocks (2 s, 2 s + 1) mod 4 of panel s / 2
     auto issue = [&](int s) {
@@ -204,10 +225,10 @@ __global__ void __launch_bounds__(kCfThreads, 4) chol_fused_panel_kernel(const C
     // (64 on the A side, 32 on the B side) come into shared memory with one round of cp.async -- the third
     // ring slot and the Dinv buffer are free until the operand stream / the epilogue need them -- instead of
     // Q/4 rounds of dependent L2 loads per warp (which were most of a CTA's life in the first panels).
-    const bool stage_u = !DENSE && 64 * Qp <= kCfStageDoubles && 32 * Qp <= kCfNB * kCfLd;
+    const bool stage_u = !DENSE && 64 * Qp <= kCfStageDoubles && 32 * Qp <= kCfUbDoubles;
     if (stage_u) {
       double* UA = ring + 2 * kCfStageDoubles;     // [64][Qp]
-      double* UB = Dv;                             // [32][Qp]
+      double* UB = Ubuf;                           // [32][Qp]
       const double* srcA = prm.UT + (size_t)r0 * Qp;
       const double* srcB = prm.UT + (size_t)J * Qp;
       for (int idx = tid; idx < Rv * Qp / 2; idx += kCfThreads) cp_async16(UA + 2 * idx, srcA + 2 * idx);
@@ -291,16 +312,11 @@ __global__ void __launch_bounds__(kCfThreads, 4) chol_fused_panel_kernel(const C
       }
     }
     cf_stamp(prm, J, w, 1);
-    pdl_wait_prior_grids();          // Dinv_J is final
-    __syncthreads();     // every warp has left the rank-Q term and the operand stream: Dv and the ring are free
-    {
-      const double* dw = prm.dinv + (size_t)w * kCfNB * kCfNB;
-      for (int idx = tid; idx < kCfNB * 16; idx += kCfThreads) {
-        const int r = idx >> 4, c2 = idx & 15;
-        cp_async16(Dv + r * kCfLd + 2 * c2, dw + r * kCfNB + 2 * c2);
-      }
-      cp_async_commit();
+    if (!early) {
+      pdl_wait_prior_grids();          // Dinv_J is final
+      fetch_dinv();
     }
+    __syncthreads();     // every warp has left the operand stream: the ring is free
     // park the tile over the ring, rows <- rows Dinv^T (Dinv lower triangular: k blocks kk <= nbk only)
     double* T = ring;
     if (active) {
@@ -347,6 +363,10 @@ __global__ void __launch_bounds__(kCfThreads, 4) chol_fused_panel_kernel(const C
 
   // ======================= tile 0: rows Jd .. Jd + 31, the next diagonal block =========================
   const int Jd = J + kCfNB;                       // first row / column of the diagonal block handled here
+  // rows 8 wr .. 8 wr + 7 belong to this warp.  The diagonal block costs warp wr (wr + 1) of the 4 column
+  // blocks, and warp i of every CTA sits on SM sub-partition i: the roles rotate with the walker, so that the
+  // heavy rows do not all land on the same FP64 pipe.
+  const int wr = (warp + (int)w) & 3;
   const int nb = min(kCfNB, M - Jd);              // its true size (identity padded to 32)
   const int Rv0 = min(kCfNB, Mg - Jd);            // rows that exist in the storage (16 or 32)
   const bool is_last = Jd + kCfNB >= M;
@@ -355,7 +375,7 @@ __global__ void __launch_bounds__(kCfThreads, 4) chol_fused_panel_kernel(const C
   pdl_launch_dependents();
   // the prologue launch follows kernels outside the chain (z_var, mean, skip, a dense source): it waits
   // before it reads anything
-  if (!has_panel || (prm.flags & 1)) pdl_wait_prior_grids();
+  if (!has_panel || early) pdl_wait_prior_grids();
   double accp[4][2], accd[4][2];                  // warp: rows 8 warp .. 8 warp + 7, 32 columns each
   {
     const double* Fpan = prm.Fp + (has_panel ? cf_panel_off(Mg, K) : 0);
@@ -364,11 +384,11 @@ __global__ void __launch_bounds__(kCfThreads, 4) chol_fused_panel_kernel(const C
     for (int nbk = 0; nbk < 4; nbk++) {
       double2 v = make_double2(0.0, 0.0), d;
       if (DENSE) {
-        if (has_panel) v = cf_dense_pair(prm, w, Jd + 8 * warp + g, J + 8 * nbk + 2 * t);
-        d = cf_dense_pair(prm, w, Jd + 8 * warp + g, Jd + 8 * nbk + 2 * t);   // (padding: identity, set below)
+        if (has_panel) v = cf_dense_pair(prm, w, Jd + 8 * wr + g, J + 8 * nbk + 2 * t);
+        d = cf_dense_pair(prm, w, Jd + 8 * wr + g, Jd + 8 * nbk + 2 * t);   // (padding: identity, set below)
       } else {
-        if (has_panel && 8 * warp < Rv0) v = ldg2(Fpan + ((size_t)nbk * RkJ + 8 * warp + g) * 8 + 2 * t);
-        d = ldg2(Fdb + (size_t)(8 * warp + g) * kCfNB + 8 * nbk + 2 * t);
+        if (has_panel && 8 * wr < Rv0) v = ldg2(Fpan + ((size_t)nbk * RkJ + 8 * wr + g) * 8 + 2 * t);
+        d = ldg2(Fdb + (size_t)(8 * wr + g) * kCfNB + 8 * nbk + 2 * t);
       }
       accp[nbk][0] = v.x;
       accp[nbk][1] = v.y;
@@ -378,6 +398,7 @@ __global__ void __launch_bounds__(kCfThreads, 4) chol_fused_panel_kernel(const C
   }
   if (prm.skip != nullptr && __ldcg(prm.skip + w)) return;
   __syncthreads();
+  if (early) fetch_dinv();
 
   auto issue0 = [&](int s) {
     if (s < nst && warp == 0) {
@@ -437,17 +458,17 @@ __global__ void __launch_bounds__(kCfThreads, 4) chol_fused_panel_kernel(const C
     for (int s6 = 0; s6 < 6; s6++)
       if (4 * s6 < Qp) {
         const int k = 4 * s6 + t;
-        const double a = vk[s6] * UA[(8 * warp + g) * Qp + k];
+        const double a = vk[s6] * UA[(8 * wr + g) * Qp + k];
 #pragma unroll
         for (int nbk = 0; nbk < 4; nbk++) {
           if (has_panel) dmma884(accp[nbk][0], accp[nbk][1], a, UB[(8 * nbk + g) * Qp + k]);
-          if (nbk <= warp) dmma884(accd[nbk][0], accd[nbk][1], a, UA[(8 * nbk + g) * Qp + k]);
+          if (nbk <= wr) dmma884(accd[nbk][0], accd[nbk][1], a, UA[(8 * nbk + g) * Qp + k]);
         }
       }
   } else if (!DENSE) {
     // rank-Q term for both tiles
     const double* zv = prm.z_var + w * prm.ldz;
-    const int row = min(Jd + 8 * warp + g, Mg - 1);
+    const int row = min(Jd + 8 * wr + g, Mg - 1);
     for (int k0 = 0; k0 < Qp; k0 += 4) {
       const double vk = (k0 + t < prm.Q) ? __ldcg(zv + k0 + t) : 0.0;
       const double a = vk * __ldg(prm.UT + (size_t)row * Qp + k0 + t);
@@ -457,7 +478,7 @@ __global__ void __launch_bounds__(kCfThreads, 4) chol_fused_panel_kernel(const C
           const double bp = __ldg(prm.UT + (size_t)(J + 8 * nbk + g) * Qp + k0 + t);
           dmma884(accp[nbk][0], accp[nbk][1], a, bp);
         }
-        if (nbk <= warp) {
+        if (nbk <= wr) {
           const double bd = __ldg(prm.UT + (size_t)min(Jd + 8 * nbk + g, Mg - 1) * Qp + k0 + t);
           dmma884(accd[nbk][0], accd[nbk][1], a, bd);
         }
@@ -472,23 +493,23 @@ __global__ void __launch_bounds__(kCfThreads, 4) chol_fused_panel_kernel(const C
     const double* B = A + 2 * kCfRows * 8;
 #pragma unroll
     for (int sub = 0; sub < 2; sub++) {
-      const double2 a = *reinterpret_cast<const double2*>(A + ((size_t)sub * kCfNB + 8 * warp + g) * 8 + 2 * t);
-      // (of the diagonal block only the lower triangle is needed: column blocks nbk <= warp)
+      const double2 a = *reinterpret_cast<const double2*>(A + ((size_t)sub * kCfNB + 8 * wr + g) * 8 + 2 * t);
+      // (of the diagonal block only the lower triangle is needed: column blocks nbk <= wr)
       double2 bp[4], bd[4];
 #pragma unroll
       for (int nbk = 0; nbk < 4; nbk++) {
         bp[nbk] = *reinterpret_cast<const double2*>(B + ((size_t)sub * kCfNB + 8 * nbk + g) * 8 + 2 * t);
-        if (nbk <= warp) bd[nbk] = *reinterpret_cast<const double2*>(A + ((size_t)sub * kCfNB + 8 * nbk + g) * 8 + 2 * t);
+        if (nbk <= wr) bd[nbk] = *reinterpret_cast<const double2*>(A + ((size_t)sub * kCfNB + 8 * nbk + g) * 8 + 2 * t);
       }
 #pragma unroll
       for (int nbk = 0; nbk < 4; nbk++) {
         dmma884(accp[nbk][0], accp[nbk][1], -a.x, bp[nbk].x);
-        if (nbk <= warp) dmma884(accd[nbk][0], accd[nbk][1], -a.x, bd[nbk].x);
+        if (nbk <= wr) dmma884(accd[nbk][0], accd[nbk][1], -a.x, bd[nbk].x);
       }
 #pragma unroll
       for (int nbk = 0; nbk < 4; nbk++) {
         dmma884(accp[nbk][0], accp[nbk][1], -a.y, bp[nbk].y);
-        if (nbk <= warp) dmma884(accd[nbk][0], accd[nbk][1], -a.y, bd[nbk].y);
+        if (nbk <= wr) dmma884(accd[nbk][0], accd[nbk][1], -a.y, bd[nbk].y);
       }
       const double2 lv = *reinterpret_cast<const double2*>(A + ((size_t)sub * kCfNB + rr) * 8 + 2 * part);
       const double2 tv2 = *reinterpret_cast<const double2*>(tvs + 16 * s + 8 * sub + 2 * part);
@@ -504,13 +525,10 @@ __global__ void __launch_bounds__(kCfThreads, 4) chol_fused_panel_kernel(const C
   }
   cf_stamp(prm, J, w, 1);
   if (has_panel) {
-    pdl_wait_prior_grids();          // Dinv_J and t[J:J+32] are final
-    const double* dw = prm.dinv + (size_t)w * kCfNB * kCfNB;
-    for (int idx = tid; idx < kCfNB * 16; idx += kCfThreads) {
-      const int r = idx >> 4, c2 = idx & 15;
-      cp_async16(Dv + r * kCfLd + 2 * c2, dw + r * kCfNB + 2 * c2);
+    if (!early) {
+      pdl_wait_prior_grids();          // Dinv_J and t[J:J+32] are final
+      fetch_dinv();
     }
-    cp_async_commit();
     if (tid < kCfNB) tvs[J + tid] = __ldcg(prm.tvec + (size_t)w * Mg + J + tid);
   }
   cp_async_wait<0>();
@@ -520,11 +538,11 @@ __global__ void __launch_bounds__(kCfThreads, 4) chol_fused_panel_kernel(const C
   if (has_panel) {
 #pragma unroll
     for (int nbk = 0; nbk < 4; nbk++)
-      *reinterpret_cast<double2*>(&T[(8 * warp + g) * kCfLd + 8 * nbk + 2 * t]) = make_double2(accp[nbk][0], accp[nbk][1]);
+      *reinterpret_cast<double2*>(&T[(8 * wr + g) * kCfLd + 8 * nbk + 2 * t]) = make_double2(accp[nbk][0], accp[nbk][1]);
     __syncwarp();
     double2 a[4];
 #pragma unroll
-    for (int kk = 0; kk < 4; kk++) a[kk] = *reinterpret_cast<const double2*>(&T[(8 * warp + g) * kCfLd + 8 * kk + 2 * t]);
+    for (int kk = 0; kk < 4; kk++) a[kk] = *reinterpret_cast<const double2*>(&T[(8 * wr + g) * kCfLd + 8 * kk + 2 * t]);
     double acc2[4][2];
 #pragma unroll
     for (int nbk = 0; nbk < 4; nbk++) acc2[nbk][0] = acc2[nbk][1] = 0.0;
@@ -539,29 +557,29 @@ __global__ void __launch_bounds__(kCfThreads, 4) chol_fused_panel_kernel(const C
       for (int nbk = kk; nbk < 4; nbk++) dmma884(acc2[nbk][0], acc2[nbk][1], a[kk].y, b[nbk].y);
     }
     __syncwarp();    // every lane of this warp has read its rows of T
-    const bool row_ok = 8 * warp < Rv0;   // (rows past the storage are neither written nor used)
+    const bool row_ok = 8 * wr < Rv0;   // (rows past the storage are neither written nor used)
     double* Lpan = Lw + cf_panel_off(Mg, K);
 #pragma unroll
     for (int nbk = 0; nbk < 4; nbk++) {
       const double2 v = row_ok ? make_double2(acc2[nbk][0], acc2[nbk][1]) : make_double2(0.0, 0.0);
-      *reinterpret_cast<double2*>(&T[(8 * warp + g) * kCfLd + 8 * nbk + 2 * t]) = v;
-      if (row_ok) *reinterpret_cast<double2*>(Lpan + ((size_t)nbk * RkJ + 8 * warp + g) * 8 + 2 * t) = v;
+      *reinterpret_cast<double2*>(&T[(8 * wr + g) * kCfLd + 8 * nbk + 2 * t]) = v;
+      if (row_ok) *reinterpret_cast<double2*>(Lpan + ((size_t)nbk * RkJ + 8 * wr + g) * 8 + 2 * t) = v;
     }
     __syncthreads();   // T = L[rows, J:J+32] complete
     // D -= L[rows, J:J+32] L[rows, J:J+32]^T;  rhs -= L[rows, J:J+32] t[J:J+32]
 #pragma unroll
     for (int kk = 0; kk < 4; kk++) {
-      const double2 a2 = *reinterpret_cast<const double2*>(&T[(8 * warp + g) * kCfLd + 8 * kk + 2 * t]);
+      const double2 a2 = *reinterpret_cast<const double2*>(&T[(8 * wr + g) * kCfLd + 8 * kk + 2 * t]);
       double2 b[4];
 #pragma unroll
       for (int nbk = 0; nbk < 4; nbk++)
-        if (nbk <= warp) b[nbk] = *reinterpret_cast<const double2*>(&T[(8 * nbk + g) * kCfLd + 8 * kk + 2 * t]);
+        if (nbk <= wr) b[nbk] = *reinterpret_cast<const double2*>(&T[(8 * nbk + g) * kCfLd + 8 * kk + 2 * t]);
 #pragma unroll
       for (int nbk = 0; nbk < 4; nbk++)
-        if (nbk <= warp) dmma884(accd[nbk][0], accd[nbk][1], -a2.x, b[nbk].x);
+        if (nbk <= wr) dmma884(accd[nbk][0], accd[nbk][1], -a2.x, b[nbk].x);
 #pragma unroll
       for (int nbk = 0; nbk < 4; nbk++)
-        if (nbk <= warp) dmma884(accd[nbk][0], accd[nbk][1], -a2.y, b[nbk].y);
+        if (nbk <= wr) dmma884(accd[nbk][0], accd[nbk][1], -a2.y, b[nbk].y);
     }
 #pragma unroll
     for (int c = 0; c < 8; c++) racc = fma(T[rr * kCfLd + 8 * part + c], tvs[J + 8 * part + c], racc);
@@ -573,7 +591,7 @@ __global__ void __launch_bounds__(kCfThreads, 4) chol_fused_panel_kernel(const C
   {
     // (not into dinv: the regular tiles of this walker may still have to read Dinv_J from there)
     double* dw = prm.draw + (size_t)w * kCfNB * kCfNB;
-    const int r = 8 * warp + g;
+    const int r = 8 * wr + g;
 #pragma unroll
     for (int nbk = 0; nbk < 4; nbk++) {
       const int c = 8 * nbk + 2 * t;

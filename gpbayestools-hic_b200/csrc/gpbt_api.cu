@@ -1,5 +1,6 @@
 // C ABI of libgpbt_b200.so (declared in include/gpbt.h): handle management, state upload with the
 // padding the kernels want, launch configuration and the host-buffer convenience entry point.
+#include <functional>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
@@ -119,16 +120,19 @@ struct Options {
   std::atomic<int64_t> fanout_min_rows{0};  // 0 = built-in default
   std::atomic<int64_t> chol_batch{0};       // walkers per sub-batch of the fused Cholesky, 0 = automatic
   std::atomic<int64_t> chol_streams{0};     // streams the fused Cholesky spreads its sub-batches over, 0 = automatic
+  std::atomic<int64_t> chol_pipe{0};        // dense path: sub-batches kernel (a) is pipelined over, 0 = automatic, 1 = off
+  std::atomic<int> chol_lag{0};             // 1: sub-batch b + 1 starts behind the first factor kernel of sub-batch b
+  std::atomic<int> chol_prio{0};            // 1: aux streams of the fused Cholesky at the highest stream priority
   std::atomic<int> cf_debug{0};             // record clock64 stamps of the fused Cholesky (tuning tool)
 };
 Options g_opt;
 long long* g_cf_dbg = nullptr;            // managed buffer of the fused Cholesky's timing stamps (option cf_debug)
 constexpr size_t kCfDbgBytes = 16 * 32 * 8 * 8 * sizeof(long long);
-constexpr int kCfMaxStreams = 4;
+constexpr int kCfMaxStreams = 5;
 // aux streams / events the fused Cholesky spreads its sub-batches over (see launch_chol_fused)
 struct FusedStreams {
-  cudaStream_t aux[kCfMaxStreams] = {nullptr, nullptr, nullptr, nullptr};   // [0] unused: the caller's stream
-  cudaEvent_t done[kCfMaxStreams] = {nullptr, nullptr, nullptr, nullptr}, fork = nullptr;
+  cudaStream_t aux[kCfMaxStreams] = {};   // [0] unused: the caller's stream
+  cudaEvent_t done[kCfMaxStreams] = {}, fork = nullptr;
   void destroy() {
     for (int i = 0; i < kCfMaxStreams; i++) {
       if (aux[i]) cudaStreamDestroy(aux[i]);
@@ -162,6 +166,12 @@ int set_option_value(const char* key, const char* value) {
     g_opt.chol_batch = v ? atoll(v) : 0;
   } else if (k == "chol_streams") {
     g_opt.chol_streams = v ? atoll(v) : 0;
+  } else if (k == "chol_pipe") {
+    g_opt.chol_pipe = v ? atoll(v) : 0;
+  } else if (k == "chol_lag") {
+    g_opt.chol_lag = v ? atoi(v) : 0;
+  } else if (k == "chol_prio") {
+    g_opt.chol_prio = v ? atoi(v) : 0;
   } else if (k == "cf_debug") {
     g_opt.cf_debug = v ? atoi(v) : 0;
   } else {
@@ -176,7 +186,7 @@ struct OptionsFromEnvironment {
         {"GPBT_PC_TILE", "pc_tile"}, {"GPBT_CHOL", "chol"}, {"GPBT_LOWRANK_GENERIC", "lowrank_generic"},
         {"GPBT_NO_ZEROCOPY", "no_zerocopy"}, {"GPBT_ENSEMBLE_SPLIT_KERNELS", "ensemble_split_kernels"},
         {"GPBT_FANOUT_MIN_ROWS", "fanout_min_rows"}, {"GPBT_CHOL_BATCH", "chol_batch"},
-        {"GPBT_CHOL_STREAMS", "chol_streams"}};
+        {"GPBT_CHOL_STREAMS", "chol_streams"}, {"GPBT_CHOL_PIPE", "chol_pipe"}};
     for (const auto& n : names)
       if (const char* e = getenv(n[0])) set_option_value(n[1], e);
   }
@@ -490,8 +500,10 @@ int launch_pc_predict_p(const PcPredictParams& prm, cudaStream_t st) {
 // measured 0.86 ms vs 0.94 ms for one 32-wide CTA per SM at config 2.  32 is used when two 16-wide
 // CTAs do not fit in shared memory; 8 for small batches (more CTAs, lower latency).
 // GPBT_PC_TILE=8|16|32 overrides (tuning / tests).
+// tile_rows: the batch size the tile width is chosen for (a caller that splits one batch into sub-batches
+// passes the size of the whole, so that the split does not change a single bit of the result).
 template <int KIND>
-int dispatch_pc_predict(const PcPredictParams& prm, cudaStream_t st) {
+int dispatch_pc_predict(const PcPredictParams& prm, cudaStream_t st, int64_t tile_rows) {
   const DeviceInfo& di = device_info();
   const size_t limit = (size_t)di.smem_optin;
   const size_t per_sm = (size_t)di.smem_per_sm - 2048;
@@ -503,7 +515,7 @@ int dispatch_pc_predict(const PcPredictParams& prm, cudaStream_t st) {
   if (tw == 8 && pc_predict_smem_bytes<8>(prm.n_pad, prm.p_pad) > limit)
     return fail(GPBT_ESHAPE, "pc_predict: n = %d design points do not fit in shared memory", prm.n);
   const int64_t want = 2 * di.sm_count;
-  while (tw > 8 && ((prm.N + tw - 1) / tw) * prm.q < want) tw >>= 1;
+  while (tw > 8 && ((tile_rows + tw - 1) / tw) * prm.q < want) tw >>= 1;
   if (const int v = g_opt.pc_tile.load()) tw = v;
   if (tw == 32) return launch_pc_predict_p<32, KIND>(prm, st);
   if (tw == 16) return launch_pc_predict_p<16, KIND>(prm, st);
@@ -511,8 +523,9 @@ int dispatch_pc_predict(const PcPredictParams& prm, cudaStream_t st) {
 }
 
 int run_pc_predict(gpbt_emulator_t e, const double* X, const double* extra, double* zm, double* zv,
-                   int64_t ldz, int64_t N, cudaStream_t st) {
+                   int64_t ldz, int64_t N, cudaStream_t st, int64_t tile_rows = 0) {
   if (N <= 0) return 0;
+  if (tile_rows < N) tile_rows = N;
   if (e->has_trafo) {
     if (N > e->theta_cap) {
       // (stream-ordered work that still reads the old buffer has been enqueued before this free;
@@ -536,9 +549,9 @@ int run_pc_predict(gpbt_emulator_t e, const double* X, const double* extra, doub
   prm.W = e->W; prm.sig2 = e->sig2; prm.z_mean = zm; prm.z_var = zv; prm.ldz = ldz; prm.N = N;
   prm.p = e->p; prm.p_pad = e->p_pad; prm.n = e->n; prm.n_pad = e->n_pad; prm.q = e->q;
   switch (e->kind) {
-    case GPBT_KERNEL_RBF: return dispatch_pc_predict<0>(prm, st);
-    case GPBT_KERNEL_MATERN32: return dispatch_pc_predict<1>(prm, st);
-    default: return dispatch_pc_predict<2>(prm, st);
+    case GPBT_KERNEL_RBF: return dispatch_pc_predict<0>(prm, st, tile_rows);
+    case GPBT_KERNEL_MATERN32: return dispatch_pc_predict<1>(prm, st, tile_rows);
+    default: return dispatch_pc_predict<2>(prm, st, tile_rows);
   }
 }
 
@@ -1153,9 +1166,14 @@ int ensure_fused(gpbt_chain* ch, int64_t rows) {
 // streams (the caller's + aux[1..]): while one sub-batch is in its factor kernel or in the tail of a panel
 // launch, the DMMA work of another fills the machine.  Options "chol_streams" / "chol_batch" override the
 // defaults.  prm carries everything but the debugging fields.
-int launch_chol_fused(CholFusedParams prm, int64_t N, FusedStreams* fs, cudaStream_t st) {
+// produce(w0, nw): enqueue on the caller's stream whatever fills z_var / mean of walkers [w0, w0 + nw)
+using FusedProduce = std::function<int(int64_t, int64_t)>;
+
+int launch_chol_fused(CholFusedParams prm, int64_t N, FusedStreams* fs, cudaStream_t st,
+                      const FusedProduce* produce = nullptr) {
   prm.dbg = nullptr;
   prm.flags = g_opt.cf_debug.load() >> 4;      // (cf_debug = 16 * flags + record-stamps bit)
+  prm.early_after = device_info().sm_count * kCfCtasPerSm;   // the CTAs that can be resident at once
   if (g_opt.cf_debug.load() & 1) {
     if (!g_cf_dbg) CU(cudaMallocManaged(&g_cf_dbg, kCfDbgBytes));
     prm.dbg = g_cf_dbg;
@@ -1169,29 +1187,64 @@ int launch_chol_fused(CholFusedParams prm, int64_t N, FusedStreams* fs, cudaStre
     return r;
   if (int r = ensure_dynamic_smem<chol_fused_factor_kernel>(kCfFactorSmem)) return r;
   void (*panel)(CholFusedParams, int, int64_t) = dense ? chol_fused_panel_kernel<true> : chol_fused_panel_kernel<false>;
+  // Pipelined form (option "chol_pipe" = number of sub-batches; off by default): the producer -- kernel (a) and
+  // the mean -- runs per sub-batch on the caller's stream, the Cholesky launches of sub-batch b follow on an
+  // aux stream as soon as ITS inputs are there, so kernel (a) of sub-batch b + 1 shares the machine with the
+  // panel launches of sub-batch b instead of running in front of all of them.  Measured at config 2, 4096
+  // walkers, best of 20 on three boxes: 3.44 ms against 3.38 ms for kernel (a) once + two sub-batches side by
+  // side -- two kernel-(a) CTAs hold all 64 K registers of an SM, so the kernels never share an SM, they take
+  // turns, and the last sub-batch ends alone.  (One box ran the side-by-side form at 3.65 ms in every
+  // repetition -- see "chol_lag" -- and the pipelined form at 3.49.)
+  int64_t pipe = produce ? g_opt.chol_pipe.load() : 1;
+  if (pipe <= 0) pipe = 1;
+  const bool pipelined = pipe > 1;
+  if (produce && !pipelined)
+    if (int r = (*produce)(0, N)) return r;
   int n_streams = (int)g_opt.chol_streams.load();
-  if (n_streams <= 0) n_streams = N >= 2048 ? 2 : 1;
-  n_streams = std::min(n_streams, kCfMaxStreams);
+  if (n_streams <= 0) n_streams = pipelined ? kCfMaxStreams - 1 : (N >= 2048 ? 2 : 1);
+  n_streams = std::min(n_streams, pipelined ? kCfMaxStreams - 1 : kCfMaxStreams);
   int64_t batch = g_opt.chol_batch.load();
-  if (batch <= 0) batch = std::max<int64_t>(512, (N + n_streams - 1) / n_streams);
+  if (pipelined) batch = round_up((N + pipe - 1) / pipe, 64);   // (whole walker tiles of kernel (a))
+  else if (batch <= 0) batch = std::max<int64_t>(512, (N + n_streams - 1) / n_streams);
   batch = std::min<int64_t>(batch, 32768);          // grid.y carries the walker
   const int64_t n_batches = (N + batch - 1) / batch;
   n_streams = (int)std::min<int64_t>(n_streams, n_batches);
-  if (n_streams > 1) {
-    for (int i = 1; i < n_streams; i++)
+  const int first_aux = pipelined ? 0 : 1;          // pipelined: every sub-batch on an aux stream
+  if (n_streams > first_aux) {
+    int prio_least = 0, prio_greatest = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    for (int i = 1; i < n_streams + 1 - first_aux; i++)
       if (!fs->aux[i]) {
-        CU(cudaStreamCreateWithFlags(&fs->aux[i], cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithPriority(&fs->aux[i], cudaStreamNonBlocking, g_opt.chol_prio.load() ? prio_greatest : prio_least));
         CU(cudaEventCreateWithFlags(&fs->done[i], cudaEventDisableTiming));
       }
     if (!fs->fork) CU(cudaEventCreateWithFlags(&fs->fork, cudaEventDisableTiming));
-    CU(cudaEventRecord(fs->fork, st));
-    for (int i = 1; i < n_streams; i++) CU(cudaStreamWaitEvent(fs->aux[i], fs->fork, 0));
+    if (!pipelined) {
+      CU(cudaEventRecord(fs->fork, st));
+      for (int i = 1; i < n_streams; i++) CU(cudaStreamWaitEvent(fs->aux[i], fs->fork, 0));
+    }
   }
+  // Sub-batches that start at the same instant can stay in lockstep: their factor kernels (a few warps per
+  // SM, latency bound, ~20 us each) then coincide instead of hiding behind the other one's panel launch --
+  // 0.2 ms per 4096 walkers on one of four boxes.  Option "chol_lag" (off by default) starts a sub-batch one
+  // step behind its predecessor, after that one's first factor kernel; it costs 0.06 ms where there is no
+  // lockstep to break (3.44 against 3.38 ms, best of 20).
+  const bool lag = !pipelined && n_streams > 1 && g_opt.chol_lag.load();
   for (int64_t b = 0; b < n_batches; b++) {
     const int64_t w0 = b * batch, nw = std::min(batch, N - w0);
-    cudaStream_t sb = (b % n_streams == 0) ? st : fs->aux[b % n_streams];
+    cudaStream_t sb;
+    if (pipelined) {
+      sb = fs->aux[1 + b % n_streams];
+      if (int r = (*produce)(w0, nw)) return r;
+      CU(cudaEventRecord(fs->fork, st));          // (a wait takes the event as recorded now: one event serves all)
+      CU(cudaStreamWaitEvent(sb, fs->fork, 0));
+    } else {
+      sb = (b % n_streams == 0) ? st : fs->aux[b % n_streams];
+    }
+    if (lag && b > 0 && b < n_streams) CU(cudaStreamWaitEvent(sb, fs->fork, 0));
     for (int J = -kCfNB; J + kCfNB < Mg; J += kCfNB) {
       const int tiles = (J >= 0 && Mg > J + 2 * kCfNB) ? (Mg - J - 2 * kCfNB + kCfRows - 1) / kCfRows : 0;
+      if (J == 0 && lag && b + 1 < n_streams) CU(cudaEventRecord(fs->fork, sb));   // (behind factor(0))
       if (prm.flags & 4) {   // plain stream order, no programmatic launch
         panel<<<dim3((unsigned)(1 + tiles), (unsigned)nw), kCfThreads, smem, sb>>>(prm, J, w0);
         LAUNCH_CHECK();
@@ -1207,17 +1260,15 @@ int launch_chol_fused(CholFusedParams prm, int64_t N, FusedStreams* fs, cudaStre
       LAUNCH_CHECK();
     }
   }
-  for (int i = 1; i < n_streams; i++) {
+  for (int i = 1; i < n_streams + 1 - first_aux; i++) {
     CU(cudaEventRecord(fs->done[i], fs->aux[i]));
     CU(cudaStreamWaitEvent(st, fs->done[i], 0));
   }
   return 0;
 }
 
-// (Running kernel (a) per sub-batch on the sub-batch's stream, so that it overlaps another sub-batch's
-// Cholesky launches, was measured: no gain -- 3.47 vs 3.49 ms at N = 4096 -- and it makes the result depend
-// on the split through kernel (a)'s walker-tile width.  Kernel (a) runs once for the whole chunk.)
-int run_chol_fused(gpbt_chain* ch, double* lp, int* n_notpd, double notpd_value, int64_t N, cudaStream_t st) {
+int run_chol_fused(gpbt_chain* ch, double* lp, int* n_notpd, double notpd_value, int64_t N, cudaStream_t st,
+                   const FusedProduce* produce = nullptr) {
   CholFusedParams prm;
   prm.Fp = ch->cf_Fp; prm.Fd = ch->cf_Fd; prm.UT = ch->cf_UT; prm.cov_src = nullptr; prm.cov_add = nullptr; prm.dense_vec = 0;
   prm.z_var = ch->z_var; prm.mean = ch->cf_mean;
@@ -1225,7 +1276,7 @@ int run_chol_fused(gpbt_chain* ch, double* lp, int* n_notpd, double notpd_value,
   prm.logdet = ch->cf_logdet; prm.tsq = ch->cf_tsq; prm.bad = ch->cf_bad; prm.lp = lp; prm.n_notpd = n_notpd;
   prm.notpd_value = notpd_value; prm.add_const = kSysConst; prm.N = N; prm.Lstride = ch->Lstride; prm.ldz = ch->Q;
   prm.M = ch->M; prm.Mg = ch->Mg; prm.Q = ch->Q; prm.Qp = ch->Qp;
-  return launch_chol_fused(prm, N, &ch->cf_fs, st);
+  return launch_chol_fused(prm, N, &ch->cf_fs, st, produce);
 }
 
 // Stand-alone batched mvn_loglike on materialised covariances through the same kernels (dense source).
@@ -1282,20 +1333,23 @@ void release_fused_dense(int device, cudaStream_t st) {
 }
 
 // Chain._predict into (mean, cov) for rows [0, N) of X; cov may be null
+// (row0 / tile_rows: X, mean and cov are those of rows [row0, row0 + N) of a batch of tile_rows rows whose
+// PC-space work rows the chain holds from row 0 -- the pipelined dense path)
 int chain_predict_rows(gpbt_chain* ch, const double* X, double extra_scale, double* mean, double* cov,
-                       int64_t N, cudaStream_t st, bool with_exp = false) {
-  if (int r = ensure_rows(ch, N)) return r;
+                       int64_t N, cudaStream_t st, bool with_exp = false, int64_t row0 = 0, int64_t tile_rows = 0) {
+  if (int r = ensure_rows(ch, row0 + N)) return r;
   const double* extra = nullptr;
   if (extra_scale != 0.0) {
-    extra_std_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(X, ch->p, N, extra_scale, ch->extra);
+    extra_std_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(X, ch->p, N, extra_scale, ch->extra + row0);
     LAUNCH_CHECK();
-    extra = ch->extra;
+    extra = ch->extra + row0;
   }
   for (size_t e = 0; e < ch->emus.size(); e++) {
     gpbt_emulator_t emu = ch->emus[e];
-    if (int r = run_pc_predict(emu, X, extra, ch->z_mean + ch->q_off[e], ch->z_var + ch->q_off[e], ch->Q, N, st))
-      return r;
-    if (int r = run_backtransform(emu, ch->z_mean + ch->q_off[e], ch->z_var + ch->q_off[e], ch->Q, mean, ch->M,
+    double* zm = ch->z_mean + row0 * ch->Q + ch->q_off[e];
+    double* zv = ch->z_var + row0 * ch->Q + ch->q_off[e];
+    if (int r = run_pc_predict(emu, X, extra, zm, zv, ch->Q, N, st, tile_rows)) return r;
+    if (int r = run_backtransform(emu, zm, zv, ch->Q, mean, ch->M,
                                   cov, ch->M, ch->m_off[e], N, st, nullptr, with_exp ? ch->base_like[e] : nullptr))
       return r;
   }
@@ -1456,8 +1510,10 @@ int log_posterior_impl(gpbt_chain_t ch, const double* X, double oob_value, doubl
       bounds_mask_kernel<<<(unsigned)((nn + 127) / 128), 128, 0, st>>>(Xs, ch->lo, ch->hi, ch->p, nn, oob_value,
                                                                        ch->skip, lp + s);
       LAUNCH_CHECK();
-      if (int r = chain_predict_rows(ch, Xs, 0.0, ch->cf_mean, nullptr, nn, st)) return r;
-      if (int r = run_chol_fused(ch, lp + s, n_notpd, oob_value, nn, st)) return r;
+      const FusedProduce produce = [&](int64_t w0, int64_t nw) {
+        return chain_predict_rows(ch, Xs + w0 * ch->p, 0.0, ch->cf_mean + w0 * ch->M, nullptr, nw, st, false, w0, nn);
+      };
+      if (int r = run_chol_fused(ch, lp + s, n_notpd, oob_value, nn, st, &produce)) return r;
     }
     return scatter_result(lp, peers, n_peers, peer_off, N, st);
   }

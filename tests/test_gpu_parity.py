@@ -597,6 +597,15 @@ def test_fused_cholesky_path(name):
             np.testing.assert_array_equal(ch.log_target(X, -1e300, path="dense"), base)
         _lib.set_option("chol_batch", None)
         _lib.set_option("chol_streams", None)
+        # ... and so is the pipelined form (kernel (a) per sub-batch, the Cholesky launches behind it)
+        for pipe, streams, lag in ((2, None, None), (5, 2, None), (1, 3, 1)):
+            _lib.set_option("chol_pipe", pipe)
+            _lib.set_option("chol_streams", streams)
+            _lib.set_option("chol_lag", lag)
+            _lib.set_option("chol_batch", 128 if lag else None)
+            np.testing.assert_array_equal(ch.log_target(X, -1e300, path="dense"), base)
+        for k in ("chol_pipe", "chol_streams", "chol_lag", "chol_batch"):
+            _lib.set_option(k, None)
         # a full experimental covariance (couples the emulators of c1_multi): still the fused kernels
         cov_sys = goldens.cov_exp_sys(g)
         ch2 = DeviceChain(states, g["lo"], g["hi"], g["y_exp"].reshape(-1), cov_sys)
@@ -607,7 +616,7 @@ def test_fused_cholesky_path(name):
             assert np.max(np.abs(lps[fin] - g["lp_posterior_sys"][fin])) <= ABS_LP
         ch2.release()
     finally:
-        for k in ("chol", "chol_batch", "chol_streams"):
+        for k in ("chol", "chol_batch", "chol_streams", "chol_pipe", "chol_lag"):
             _lib.set_option(k, None)
     ch.release()
 

@@ -29,6 +29,10 @@ def count(label, reps, N=8192):
 _lib.set_option("chol", "fused")
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 600
 import time
+for pipe in (2, 4):
+    _lib.set_option("chol_pipe", pipe)
+    count("fused pipelined over %d sub-batches" % pipe, reps)
+_lib.set_option("chol_pipe", 1)
 for dbg in (0, 16):
     for streams, cb in ((1, 100000), (1, 512), (2, 2048), (2, 512), (3, 1024)):
         _lib.set_option("cf_debug", dbg); _lib.set_option("chol_batch", cb); _lib.set_option("chol_streams", streams)
