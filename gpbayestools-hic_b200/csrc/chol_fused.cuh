@@ -278,6 +278,7 @@ __global__ void __launch_bounds__(kCfThreads, kCfCtasPerSm) chol_fused_panel_ker
     // stream shared the SM -- 8..41 of 4.9 M evaluations, 0 of 9.8 M with this wait, 0 of 20 M with a block
     // barrier per stage; tools/r02/fused_verify.py.  The protocol reads correct either way; the cause was not
     // found, the measured-safe order is kept.)
+    if (prm.flags & 64) __syncthreads();   // (experiment: the early refill must not overtake the rank-Q term)
 #pragma unroll 1
     for (int s = 0; s < nst; s++) {
       mbar_wait(&full_bar[s % kCfStages], (s / kCfStages) & 1);
@@ -304,10 +305,12 @@ __global__ void __launch_bounds__(kCfThreads, kCfCtasPerSm) chol_fused_panel_ker
             for (int nbk = 0; nbk < 4; nbk++) dmma884(acc[mb][nbk][0], acc[mb][nbk][1], -a[mb].y, b[nbk].y);
         }
       }
+      if (prm.flags & 128) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[s % kCfStages]);
       if (warp == 0 && s + kCfStages - 1 < nst) {
-        mbar_wait(&empty_bar[s % kCfStages], (s / kCfStages) & 1);   // all four warps are done with stage s
+        if (!(prm.flags & 64)) mbar_wait(&empty_bar[s % kCfStages], (s / kCfStages) & 1);   // all four warps are done with stage s
+        else if (s >= 1) mbar_wait(&empty_bar[(s - 1) % kCfStages], ((s - 1) / kCfStages) & 1);   // (experiment: with stage s - 1)
         issue(s + kCfStages - 1);
       }
     }
@@ -516,10 +519,12 @@ __global__ void __launch_bounds__(kCfThreads, kCfCtasPerSm) chol_fused_panel_ker
       racc = fma(lv.x, tv2.x, racc);
       racc = fma(lv.y, tv2.y, racc);
     }
+    if (prm.flags & 128) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[s % kCfStages]);
     if (warp == 0 && s + kCfStages - 1 < nst) {
-      mbar_wait(&empty_bar[s % kCfStages], (s / kCfStages) & 1);   // (see the regular tile)
+      if (!(prm.flags & 64)) mbar_wait(&empty_bar[s % kCfStages], (s / kCfStages) & 1);   // (see the regular tile)
+      else if (s >= 1) mbar_wait(&empty_bar[(s - 1) % kCfStages], ((s - 1) / kCfStages) & 1);
       issue0(s + kCfStages - 1);
     }
   }
