@@ -31,7 +31,10 @@ constexpr int kCfThreads = 128;
 constexpr int kCfCtasPerSm = 4;  // by registers (128) and shared memory (54 KB)
 constexpr int kCfRows = 64;      // rows of a regular tile (16 per warp)
 constexpr int kCfStages = 3;     // ring depth, 16 columns per stage
-constexpr int kCfLd = kSpLd;     // row stride of 32-column tiles in shared memory
+constexpr int kCfLd = 40;        // row stride of the 32-column tiles (T, Dinv) in shared memory: all their fragment
+                                 // accesses are 16-byte ones at [row g][8 k + 2 t]; a quarter warp (g = 0, 1; t = 0..3)
+                                 // covers all eight 16-byte bank groups when the stride is 8 mod 16 doubles (34, the
+                                 // stride of the 8-byte fragment loads elsewhere, made every one of them 2-way)
 constexpr int kCfLdD = 34;       // row stride of the diagonal block in the factor kernel (lane = row, LDS.128 pairs)
 
 // Everything one launch of the chain hands to the next (Dinv, raw blocks, t, log-determinants, flags) and
@@ -587,7 +590,11 @@ __global__ void __launch_bounds__(kCfThreads, kCfCtasPerSm) chol_fused_panel_ker
         if (nbk <= wr) dmma884(accd[nbk][0], accd[nbk][1], -a2.y, b[nbk].y);
     }
 #pragma unroll
-    for (int c = 0; c < 8; c++) racc = fma(T[rr * kCfLd + 8 * part + c], tvs[J + 8 * part + c], racc);
+    for (int i = 0; i < 4; i++) {   // (column pairs 2 part + 8 i: conflict-free 16-byte loads)
+      const double2 lv = *reinterpret_cast<const double2*>(&T[rr * kCfLd + 2 * part + 8 * i]);
+      racc = fma(lv.x, tvs[J + 2 * part + 8 * i], racc);
+      racc = fma(lv.y, tvs[J + 2 * part + 8 * i + 1], racc);
+    }
   }
   racc += __shfl_xor_sync(0xffffffffu, racc, 1);
   racc += __shfl_xor_sync(0xffffffffu, racc, 2);
