@@ -26,6 +26,7 @@ SYMBOLS = [
     "gpbt_ensemble_prepare", "gpbt_ensemble_begin_half", "gpbt_ensemble_copy_proposals", "gpbt_ensemble_end_half", "gpbt_ensemble_read", "gpbt_ensemble_reset",
     "gpbt_device_count", "gpbt_set_device", "gpbt_get_device", "gpbt_set_option",
     "gpbt_debug_timing_read", "gpbt_debug_fused_read", "gpbt_fanout_create", "gpbt_fanout_destroy", "gpbt_fanout_size", "gpbt_fanout_log_posterior_host",
+    "gpbt_ptlmc_create", "gpbt_ptlmc_destroy", "gpbt_ptlmc_set_state", "gpbt_ptlmc_run", "gpbt_ptlmc_read",
 ]
 
 
@@ -86,6 +87,11 @@ def _load():
     lib.gpbt_fanout_destroy.argtypes = [vp]
     lib.gpbt_fanout_size.argtypes = [vp]
     lib.gpbt_fanout_log_posterior_host.argtypes = [vp, dp, dbl, dp, C.POINTER(i32), i64, i32, i32, C.POINTER(i32)]
+    lib.gpbt_ptlmc_create.argtypes = [C.POINTER(vp), vp, i32, i32, dp, dp, dbl, C.c_uint64]
+    lib.gpbt_ptlmc_destroy.argtypes = [vp]
+    lib.gpbt_ptlmc_set_state.argtypes = [vp, dp, dbl]
+    lib.gpbt_ptlmc_run.argtypes = [vp, i64, i64, i64]
+    lib.gpbt_ptlmc_read.argtypes = [vp, dp, dp, dp, dp]
     return lib
 
 

@@ -1954,3 +1954,4 @@ extern "C" int gpbt_host_temp_exchange(const double* lp, const double* temps, in
 }
 
 #include "fanout.inl"
+#include "ptlmc.inl"

@@ -298,25 +298,33 @@ class Chain:
 
     # ---- parallel tempering (src/mcmc.py:431-727) -----------------------------------------
     def samplerPTLMC(self, logpostfunc, draw_func, theta0=None, numtemps=32, numchain=16, sampperchain=400,
-                     maxtemp=30, nstartparameters=1000):
+                     maxtemp=30, nstartparameters=1000, sampler="host", seed=None):
         """Parallel-tempering (Langevin) MCMC; returns {'theta': [numchain, sampperchain, p]}.
-        See gpbt_b200.ptlmc for the algorithm."""
+        See gpbt_b200.ptlmc for the algorithm.  sampler="host" (default) is the reference's loop, draw for draw
+        from NumPy's global generator; sampler="device" keeps the chains on the GPU for the iteration loop
+        (Philox draws keyed by `seed`; logpostfunc must be this chain's log_posterior)."""
         from .ptlmc import sampler_ptlmc
+        if sampler not in ("host", "device"):
+            raise ValueError("sampler must be 'host' or 'device'")
+        dc = None
+        if sampler == "device":
+            dc = self.device(numtemps + numchain)
         return sampler_ptlmc(logpostfunc, draw_func, theta0=theta0, numtemps=numtemps, numchain=numchain,
                              sampperchain=sampperchain, maxtemp=maxtemp, nstartparameters=nstartparameters,
-                             exchange=self.tempexchange)
+                             exchange=self.tempexchange, device_chain=dc, seed=seed)
 
     def tempexchange(self, lpostf, temps, iters=1):
         from .ptlmc import temp_exchange
         return temp_exchange(lpostf, temps, iters=iters)
 
-    def run_MCMC_PTLMC(self, nsteps=500, nwalkers=16, ntemps=50, maxtemp=100, nstartparameters=1000):
+    def run_MCMC_PTLMC(self, nsteps=500, nwalkers=16, ntemps=50, maxtemp=100, nstartparameters=1000,
+                       sampler="host", seed=None):
         """PTLMC run on the GPU log-posterior (all ntemps + nwalkers chains in one call per iteration);
         the T = 1 chains are stored as chain[nwalkers, nsteps, ndim] in `mcmc_path`
-        (src/mcmc.py:696-727)."""
+        (src/mcmc.py:696-727).  sampler="device": see samplerPTLMC."""
         out = self.samplerPTLMC(logpostfunc=self.log_posterior, draw_func=self.random_pos, theta0=None,
                                 numtemps=ntemps, numchain=nwalkers, sampperchain=nsteps, maxtemp=maxtemp,
-                                nstartparameters=nstartparameters)
+                                nstartparameters=nstartparameters, sampler=sampler, seed=seed)
         self.chain = out["theta"].reshape((nwalkers, nsteps, self.ndim))
         with open(self.mcmc_path, "wb") as fh:
             pickle.dump({"chain": self.chain}, fh)

@@ -144,9 +144,86 @@ def _preoptimise(target, theta, cen, sc):
     return theta
 
 
+class DevicePTLMC:
+    """The iteration loop of the sampler with the chains resident on the GPU (gpbt_ptlmc_*, csrc/ptlmc.cuh): Gaussian
+    proposal, the chain's log-posterior path, tempered Metropolis accept, five exchange sweeps, step-size tuning and
+    the record of the T = 1 chains, without a host round trip per iteration.  Same algorithm as the loop of
+    `sampler_ptlmc` (src/mcmc.py:623-671, 679-693); the random numbers come from a counter-based Philox generator
+    keyed by `seed`, so a run is reproducible but does not follow NumPy's global stream (the host loop does).
+
+    temps: the ladder [n] (hot chains first, the T = 1 chains last), root [p, p] = C^1/2 of the proposal,
+    n_hot = number of chains above T = 1."""
+
+    def __init__(self, device_chain, temps, root, n_hot, goal=0.25, seed=None):
+        import ctypes as C
+        from . import _lib
+        self._lib = _lib
+        temps = np.ascontiguousarray(temps, dtype=np.float64).reshape(-1)
+        root = np.ascontiguousarray(root, dtype=np.float64)
+        self.n, self.p, self.n_hot = temps.shape[0], device_chain.p, int(n_hot)
+        if root.shape != (self.p, self.p):
+            raise ValueError("root must be [%d, %d]" % (self.p, self.p))
+        if seed is None:
+            seed = int(np.random.randint(0, 2 ** 31 - 1))
+        self.seed = int(seed)
+        if not device_chain._checked:
+            device_chain._self_check()
+        h = C.c_void_p()
+        _lib.check(_lib.lib.gpbt_ptlmc_create(C.byref(h), device_chain.handle(), self.n, self.n_hot, _lib.host_ptr(temps),
+                                              _lib.host_ptr(root), float(goal), C.c_uint64(self.seed)))
+        self._h, self._dc = h, device_chain
+        device_chain._dependents.add(self)
+        self.n_tune = self.n_keep = 0
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            self._lib.lib.gpbt_ptlmc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass   # interpreter shutdown
+
+    def _handle(self):
+        if self._h is None:
+            raise RuntimeError("the sampler was closed (its chain was released or rebuilt)")
+        return self._h
+
+    def set_state(self, theta, tau=-1.0):
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        if theta.shape != (self.n, self.p):
+            raise ValueError("theta must be [%d, %d]" % (self.n, self.p))
+        if not np.all(np.isfinite(theta)):
+            raise ValueError("the starting points contain non-finite coordinates")
+        self._lib.check(self._lib.lib.gpbt_ptlmc_set_state(self._handle(), self._lib.host_ptr(theta), float(tau)))
+
+    def run(self, n_tune, n_keep, n_steps=None):
+        """the next n_steps (default: all) iterations of a run of n_tune tuning + n_keep recorded iterations"""
+        self.n_tune, self.n_keep = int(n_tune), int(n_keep)
+        if n_steps is None:
+            n_steps = self.n_tune + self.n_keep
+        self._lib.check(self._lib.lib.gpbt_ptlmc_run(self._handle(), self.n_tune, self.n_keep, int(n_steps)))
+
+    def read(self):
+        """{'theta': [n - n_hot, n_keep, p] recorded T = 1 chains, 'state' [n, p], 'lp' [n], 'tau', 'stride',
+        'accepted' (proposals of the T = 1 chains taken after tuning), 'n_notpd'}"""
+        saved = np.zeros((self.n - self.n_hot, self.n_keep, self.p))
+        state, lp, info = np.empty((self.n, self.p)), np.empty(self.n), np.zeros(4)
+        hp = self._lib.host_ptr
+        self._lib.check(self._lib.lib.gpbt_ptlmc_read(self._handle(), hp(saved) if saved.size else None, hp(state), hp(lp),
+                                                      hp(info)))
+        return {"theta": saved, "state": state, "lp": lp, "tau": info[0], "stride": info[1], "accepted": int(info[2]),
+                "n_notpd": int(info[3])}
+
+
 def sampler_ptlmc(logpostfunc, draw_func, theta0=None, numtemps=32, numchain=16, sampperchain=400,
-                  maxtemp=30, nstartparameters=1000, exchange=temp_exchange):
-    """Returns {'theta': [numchain, sampperchain, p]} (src/mcmc.py:431-675)."""
+                  maxtemp=30, nstartparameters=1000, exchange=temp_exchange, device_chain=None, seed=None):
+    """Returns {'theta': [numchain, sampperchain, p]} (src/mcmc.py:431-675).
+
+    device_chain (a DeviceChain whose log-posterior logpostfunc evaluates): run the iteration loop on the GPU
+    (DevicePTLMC, Philox draws keyed by `seed`) after the start-up stage, which stays on the host either way."""
     if theta0 is None:
         theta0 = draw_func(nstartparameters)
     if theta0.shape[0] < 10 * theta0.shape[1]:        # too few candidates to rank: draw (again)
@@ -184,6 +261,19 @@ def sampler_ptlmc(logpostfunc, draw_func, theta0=None, numtemps=32, numchain=16,
         return 2 * (1 + (np.exp(2 * tau) - 1) / (np.exp(2 * tau) + 1))
 
     tau = -1
+    if device_chain is not None:
+        if target.has_grad:
+            raise ValueError("the device loop is the sampler's branch without gradients")
+        dev = DevicePTLMC(device_chain, temps, root, numtemps, goal=goal, seed=seed)
+        try:
+            dev.set_state(theta, tau=tau)
+            dev.run(n_tune, sampperchain)
+            out = dev.read()
+        finally:
+            dev.close()
+        log.info("PTLMC (device loop): tau %.3f, %d accepted proposals of the T = 1 chains in %d iterations",
+                 out["tau"], out["accepted"], sampperchain)
+        return {"theta": out["theta"]}
     rho_t = stride_of(tau) * temps ** (1 / 3)
     hits = 0
     for k in range(0, n_tune + sampperchain):

@@ -252,6 +252,34 @@ int gpbt_host_temp_exchange(const double* lp_host, const double* temps_host, int
                             const int64_t* picks_host, const double* log_u_host, int64_t n_picks,
                             int64_t* order_host);
 
+/* ---- device-resident PTLMC sampling loop ------------------------------------------------------- *
+ * Replaces the iteration loop of Chain.samplerPTLMC (src/mcmc.py:623-671, the branch without
+ * gradients, which is the one Chain.log_posterior drives) and Chain.tempexchange (:679-693): Gaussian
+ * proposal theta + sqrt(2) rho_T (xi C^1/2) with rho_T = stride(tau) T^(1/3), tempered Metropolis
+ * accept, five sweeps of random adjacent-temperature swaps, step-size tuning every tenth of the
+ * first n_tune iterations, record of the T = 1 chains afterwards.  All n_chains chains stay on the
+ * device; an iteration is proposal kernel -> log-posterior path -> one single-CTA kernel.  Random
+ * numbers are counter-based (Philox, keyed by seed): reproducible, but not NumPy's global stream
+ * (the host driver gpbt_b200/ptlmc.py follows that one draw for draw).  The start-up stage of the
+ * reference's sampler (:560-621) stays with the caller.  Synchronous, on the chain's own stream.   */
+typedef struct gpbt_ptlmc* gpbt_ptlmc_t;
+
+/* temps_host [n_chains]: the ladder, hottest first, the last n_chains - n_hot entries at T = 1;
+ * root_host [p, p]: C^1/2 of the proposal; goal: target acceptance (0.25 in the reference)        */
+int gpbt_ptlmc_create(gpbt_ptlmc_t* out, gpbt_chain_t chain, int n_chains, int n_hot, const double* temps_host,
+                      const double* root_host, double goal, uint64_t seed);
+int gpbt_ptlmc_destroy(gpbt_ptlmc_t s);
+/* starting points theta_host [n_chains, p] (their log-posteriors are evaluated here), tau: the
+ * step-size parameter (reference: -1); restarts the iteration count                               */
+int gpbt_ptlmc_set_state(gpbt_ptlmc_t s, const double* theta_host, double tau);
+/* the next n_steps iterations of a run of n_tune + n_keep                                         */
+int gpbt_ptlmc_run(gpbt_ptlmc_t s, int64_t n_tune, int64_t n_keep, int64_t n_steps);
+/* saved_host [n_chains - n_hot, n_keep, p] (the reference's sampler_info['theta']), theta_host
+ * [n_chains, p] / lp_host [n_chains] the current state, info_host[4] = {tau, stride, accepted
+ * proposals of the T = 1 chains after tuning, non-positive-definite covariances seen}; any may be
+ * NULL                                                                                            */
+int gpbt_ptlmc_read(gpbt_ptlmc_t s, double* saved_host, double* theta_host, double* lp_host, double* info_host);
+
 /* ---- single-process multi-GPU fan-out of the host boundary call -------------------------------- *
  * The reference's samplers are single-process and pass ONE host array to Chain.log_posterior /
  * log_likelihood (src/mcmc.py:188-222, 261-299; pocoMC hands over all active particles, :798-804).

@@ -352,3 +352,25 @@ def test_chain_state_key_sees_in_place_edits(tmp_path):
     assert ch._state_key(True) != ch._state_key(False) or ch._state_key(False) != k2
     ch.devices = [0]
     assert ch._state_key(False) != k2
+
+
+def test_ptlmc_oracle_exchange_is_the_pinned_sweep(monkeypatch):
+    """oracle/ptlmc_oracle.exchange_sweep (the checker of the device-resident PTLMC loop) = the sweep that is
+    pinned to the unmodified reference (gpbt_b200.ptlmc.temp_exchange_python, tests/test_ptlmc.py), on the
+    same slots and uniforms; and its Philox-keyed draws are slots in [1, n) / logs of uniforms"""
+    from oracle import ptlmc_oracle as pto
+    from gpbt_b200 import ptlmc
+    rng = np.random.default_rng(0)
+    for n in (2, 3, 37, 200):
+        lp = 5.0 * rng.normal(size=n)
+        temps = ptlmc.temperature_ladder(n - n // 4 - 1, n // 4 + 1, 25.0).ravel()
+        slots, logu = pto.sweep_draws(11, 3, 1, n)
+        assert slots.min() >= 1 and slots.max() <= n - 1 and np.all(logu <= 0.0)
+        got = pto.exchange_sweep(lp, temps, np.arange(n), slots, logu)
+        it = iter(logu)
+        monkeypatch.setattr(np.random, "choice", lambda a, k: slots)
+        monkeypatch.setattr(np.random, "uniform", lambda size=1: np.array([np.exp(next(it))]))
+        want = ptlmc.temp_exchange_python(lp, temps, iters=1)
+        monkeypatch.undo()
+        assert np.array_equal(got, want)
+    assert abs(pto.stride_of(-1.0) - 2 * (1 + np.tanh(-1.0))) < 1e-15
