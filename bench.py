@@ -733,6 +733,36 @@ def config_records(args, torch, dev, chain2, states2, g2):
         out["C3"] = {"shape": "p15 n1000 m300 q20, surmise-PCGP-shaped fit (parity unpinned: surmise absent)",
                      "rows_per_call": 8192, "evals_per_s": rate, "ms_per_call": dt * 1e3,
                      "what": "Chain.log_posterior host call, all PTLMC chains at once"}
+        # one PTLMC iteration over those 8192 chains (7168 tempered + 1024 at T = 1): the host loop of
+        # gpbt_b200.ptlmc (NumPy proposal / accept, one GPU call, exchange sweeps in the C helper) and the
+        # device-resident loop (gpbt_ptlmc_*)
+        from gpbt_b200 import ptlmc
+        n_all, n_hot, iters = 8192, 7168, 10
+        temps = ptlmc.temperature_ladder(n_hot, n_all - n_hot, 100.0)
+        root = np.diag(0.02 * (hi - lo))
+        theta = X3.copy()
+        f = chb.log_target(theta, -np.inf).reshape(-1, 1) / temps
+        np.random.seed(0)
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            prop = theta + np.sqrt(2) * temps ** (1 / 3) * (np.random.normal(0, 1, theta.shape) @ root)
+            fp = chb.log_target(prop, -np.inf).reshape(-1, 1) / temps
+            take = np.where(np.log(np.random.uniform(size=n_all)) < np.squeeze(fp - f))[0]
+            theta[take], f[take] = prop[take], fp[take]
+            flat = f * temps
+            order = ptlmc.temp_exchange(flat, temps, iters=5)
+            f, theta = flat[order] / temps, theta[order]
+        ms_host = (time.perf_counter() - t0) / iters * 1e3
+        pt = ptlmc.DevicePTLMC(chb, temps, root, n_hot, seed=1)
+        pt.set_state(X3, tau=-1.0)
+        pt.run(2 * iters, iters, n_steps=iters)           # (warm-up)
+        t0 = time.perf_counter()
+        pt.run(2 * iters, iters, n_steps=2 * iters)
+        ms_dev = (time.perf_counter() - t0) / (2 * iters) * 1e3
+        pt.close()
+        out["C3"]["ptlmc_iteration"] = {"chains": n_all, "at_T1": n_all - n_hot, "ms_host_loop": ms_host,
+                                        "ms_device_loop": ms_dev,
+                                        "what": "proposal + log-posterior of all chains + tempered accept + 5 exchange sweeps"}
         chb.release()
         stb.release()
     # fan-out: one process, several GPUs, through the same host call

@@ -15,11 +15,11 @@
 // (oracle/ptlmc_oracle.py) that the tests follow draw for draw; it does not follow NumPy's global stream --
 // the host driver (gpbt_b200/ptlmc.py) does that.
 //
-// The sweeps are sequential by definition (a swap changes what the next slot sees).  A warp takes 32 slots at a
-// time: slots that are at least two apart commute, so a window without such a pair is applied by all lanes at
-// once and equals the sequential result; a window with one is replayed lane by lane.  With n = 8192 chains four
-// windows in five are conflict free (a sweep costs ~0.05 ms instead of ~0.4 ms on a single thread); with a few
-// dozen chains every window is replayed and the sweep is a few microseconds anyway.
+// The sweeps are sequential by definition (a swap changes what the next slot sees).  Slots that are at least two
+// apart commute, so a warp takes 32 slots at a time: the lanes whose slot touches no chain of an earlier slot of
+// the window are applied at once, the others (with n = 8192 chains four windows in five have none) one by one
+// in order -- slot for slot the sequential result.  Drawing the slots (Philox, log) and finding those lanes is
+// done by all warps beforehand; the walk through the windows is a few shared-memory reads per window.
 #pragma once
 #include "common.cuh"
 #include "ensemble.cuh"
@@ -50,6 +50,9 @@ struct PtlmcParams {
   double* theta_out;                     // [n, p]
   double* lp_out;                        // [n]
   double* saved;                         // [n - n_hot, n_keep, p]
+  int* sw_slot;                          // [n]  scratch of one exchange sweep: slot,
+  double* sw_gap;                        // [n]    the ladder gap at the slot,
+  double* sw_logu;                       // [n]    log of the uniform
   long long k, n_tune, n_keep;
   double goal;
 };
@@ -96,8 +99,11 @@ __global__ void __launch_bounds__(128) ptlmc_propose_kernel(const PtlmcParams pr
   }
 }
 
-// accept + exchange + permutation + tuning + record: ONE CTA.  Shared memory: lp [n], order [n], taken [n].
-inline size_t ptlmc_step_smem_bytes(int n) { return (size_t)n * (sizeof(double) + sizeof(int) + 1) + 64; }
+// accept + exchange + permutation + tuning + record: ONE CTA.  Shared memory: lp [n], order [n], one mask per
+// window of 32 slots, taken [n].
+inline size_t ptlmc_step_smem_bytes(int n) {
+  return (size_t)n * (sizeof(double) + sizeof(int) + 1) + (size_t)((n + 31) / 32) * sizeof(unsigned int) + 64;
+}
 
 __global__ void __launch_bounds__(kPtStepThreads) ptlmc_step_kernel(const PtlmcParams prm) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -106,7 +112,8 @@ __global__ void __launch_bounds__(kPtStepThreads) ptlmc_step_kernel(const PtlmcP
   const int n = prm.n, p = prm.p;
   double* lp_s = reinterpret_cast<double*>(smem_raw);
   int* order = reinterpret_cast<int*>(lp_s + n);
-  unsigned char* taken = reinterpret_cast<unsigned char*>(order + n);
+  unsigned int* win_marked = reinterpret_cast<unsigned int*>(order + n);
+  unsigned char* taken = reinterpret_cast<unsigned char*>(win_marked + (n + 31) / 32);
   __shared__ int s_hits, s_cold_hits;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_hits = s_cold_hits = 0;
@@ -130,44 +137,69 @@ __global__ void __launch_bounds__(kPtStepThreads) ptlmc_step_kernel(const PtlmcP
   if (mine_cold) atomicAdd(&s_cold_hits, mine_cold);
   __syncthreads();
 
-  // ---- temperature exchange: kPtSweeps sweeps of n random slots, on warp 0 -----------------------
-  if (warp == 0 && n > 1) {
+  // ---- temperature exchange: kPtSweeps sweeps of n random slots -----------------------------------------
+  // Per sweep, all warps first draw the slots (Philox, log, the ladder gap of the slot) into a scratch array and
+  // mark, per window of 32 consecutive slots, the lanes whose slot touches a chain that an EARLIER slot of the
+  // window touches.  Warp 0 then walks through the windows in order: the unmarked lanes commute with everything
+  // before them in the window and with each other, so they are applied at once; the marked ones (usually none,
+  // sometimes one or two) follow one by one in lane order.  That is the sequential sweep, slot for slot.
+  if (n > 1) {
+    const int n_win = (n + 31) / 32;
     for (int sweep = 0; sweep < kPtSweeps; sweep++) {
-      for (int base = 0; base < n; base += 32) {
-        const int jdx = base + lane;
+      for (int win = warp; win < n_win; win += (int)(blockDim.x >> 5)) {
+        const int jdx = 32 * win + lane;
         const bool valid = jdx < n;
         uint32_t r[4];
         philox4x32(prm.seed, (uint64_t)prm.k, (uint32_t)jdx, kPtTagSweep + sweep, r);
         int rt = 1 + (int)(u01(r[0], r[1]) * (double)(n - 1));
         rt = min(rt, n - 1);
-        const double logu = log(u01(r[2], r[3]));
-        // does this slot touch a chain an earlier slot of the window touches?
         bool conflict = false;
         for (int d = 1; d < 32; d++) {
           const int other = __shfl_up_sync(0xffffffffu, rt, d);
-          conflict = conflict || (valid && lane >= d && abs(rt - other) <= 1);
+          conflict = conflict || (lane >= d && abs(rt - other) <= 1);
         }
-        const bool replay = __any_sync(0xffffffffu, conflict);
-        auto apply = [&]() {
+        const unsigned int marked = __ballot_sync(0xffffffffu, conflict && valid);
+        if (valid) {
+          prm.sw_slot[jdx] = rt;
+          prm.sw_logu[jdx] = log(u01(r[2], r[3]));
+          prm.sw_gap[jdx] = prm.gap[rt];
+        }
+        if (lane == 0) win_marked[win] = marked;
+      }
+      __syncthreads();
+      if (warp == 0) {
+        auto apply = [&](int rt, double gap, double logu) {
           const int a = order[rt - 1], b = order[rt];
-          if ((lp_s[b] - lp_s[a]) * prm.gap[rt] > logu) {
+          if ((lp_s[b] - lp_s[a]) * gap > logu) {
             order[rt - 1] = b;
             order[rt] = a;
           }
         };
-        if (!replay) {
-          if (valid) apply();
+        // (the draws of window w + 1 are in flight while window w is applied)
+        int rt = 1;
+        double gap = 0.0, logu = 0.0;
+        if (lane < n) { rt = prm.sw_slot[lane]; gap = prm.sw_gap[lane]; logu = prm.sw_logu[lane]; }
+        for (int win = 0; win < n_win; win++) {
+          const int jn = 32 * (win + 1) + lane;
+          int rt_n = 1;
+          double gap_n = 0.0, logu_n = 0.0;
+          if (jn < n) { rt_n = prm.sw_slot[jn]; gap_n = prm.sw_gap[jn]; logu_n = prm.sw_logu[jn]; }
+          const bool valid = 32 * win + lane < n;
+          unsigned int marked = win_marked[win];
+          if (valid && !((marked >> lane) & 1u)) apply(rt, gap, logu);
           __syncwarp();
-        } else {
-          for (int l = 0; l < 32; l++) {
-            if (lane == l && valid) apply();
+          while (marked) {
+            const int l = __ffs(marked) - 1;
+            marked &= marked - 1;
+            if (lane == l) apply(rt, gap, logu);
             __syncwarp();
           }
+          rt = rt_n; gap = gap_n; logu = logu_n;
         }
       }
+      __syncthreads();
     }
   }
-  __syncthreads();
 
   // ---- the new state, position by position: chain order[pos], moved or not ---------------------------
   for (int idx = tid; idx < n * p; idx += blockDim.x) {

@@ -13,6 +13,8 @@ struct gpbt_ptlmc {
   double *temps = nullptr, *cbrt_t = nullptr, *gap = nullptr, *root = nullptr;
   double *theta[2] = {nullptr, nullptr}, *lp[2] = {nullptr, nullptr}, *prop = nullptr, *lp_prop = nullptr;
   double* saved = nullptr;
+  int* sw_slot = nullptr;
+  double *sw_gap = nullptr, *sw_logu = nullptr;
   int64_t n_keep = 0, n_tune = 0, k = 0;      // k: iterations done in the current run
   int cur = 0;                                 // which of theta[] / lp[] holds the state
   int* notpd = nullptr;
@@ -24,7 +26,7 @@ extern "C" int gpbt_ptlmc_destroy(gpbt_ptlmc_t s) {
   cudaSetDevice(s->ch ? s->ch->device : 0);
   if (s->ch && s->ch->stream) cudaStreamSynchronize(s->ch->stream);
   void* ptrs[] = {s->ctl, s->temps, s->cbrt_t, s->gap, s->root, s->theta[0], s->theta[1], s->lp[0], s->lp[1],
-                  s->prop, s->lp_prop, s->saved, s->notpd};
+                  s->prop, s->lp_prop, s->saved, s->notpd, s->sw_slot, s->sw_gap, s->sw_logu};
   for (void* q : ptrs)
     if (q) cudaFree(q);
   delete s;
@@ -64,12 +66,15 @@ extern "C" int gpbt_ptlmc_create(gpbt_ptlmc_t* out, gpbt_chain_t ch, int n_chain
   }
   rc = rc ? rc : up(&s->prop, nullptr, (size_t)n * p);
   rc = rc ? rc : up(&s->lp_prop, nullptr, n);
+  rc = rc ? rc : up(&s->sw_gap, nullptr, n);
+  rc = rc ? rc : up(&s->sw_logu, nullptr, n);
   auto raw = [&](void** dst, size_t bytes) -> int {
     CU(cudaMalloc(dst, bytes));
     return 0;
   };
   rc = rc ? rc : raw(reinterpret_cast<void**>(&s->ctl), sizeof(PtlmcCtl));
   rc = rc ? rc : raw(reinterpret_cast<void**>(&s->notpd), sizeof(int));
+  rc = rc ? rc : raw(reinterpret_cast<void**>(&s->sw_slot), (size_t)n * sizeof(int));
   if (rc) {
     gpbt_ptlmc_destroy(s);
     return rc;
@@ -126,6 +131,7 @@ extern "C" int gpbt_ptlmc_run(gpbt_ptlmc_t s, int64_t n_tune, int64_t n_keep, in
     prm.temps = s->temps; prm.cbrt_t = s->cbrt_t; prm.gap = s->gap; prm.root = s->root;
     prm.theta_in = s->theta[s->cur]; prm.lp_in = s->lp[s->cur]; prm.prop = s->prop; prm.lp_prop = s->lp_prop;
     prm.theta_out = s->theta[s->cur ^ 1]; prm.lp_out = s->lp[s->cur ^ 1]; prm.saved = s->saved;
+    prm.sw_slot = s->sw_slot; prm.sw_gap = s->sw_gap; prm.sw_logu = s->sw_logu;
     prm.k = s->k; prm.n_tune = n_tune; prm.n_keep = n_keep; prm.goal = s->goal;
     CU(launch_pdl(ptlmc_propose_kernel, dim3((unsigned)((n + warps - 1) / warps)), warps * 32,
                   (size_t)warps * 2 * p2 * sizeof(double), st, prm));
