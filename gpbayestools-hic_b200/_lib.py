@@ -105,7 +105,8 @@ def check(rc):
 
 def set_option(key, value=None):
     """gpbt_set_option: tuning override ("pc_tile", "chol", "lowrank_generic", "no_zerocopy",
-    "ensemble_split_kernels", "fanout_min_rows", "chol_batch"); None restores the default."""
+    "ensemble_split_kernels", "fanout_min_rows", "chol_batch", "chol_streams", "chol_pipe", "chol_lag",
+    "chol_prio", "cf_debug"); None restores the default."""
     check(lib.gpbt_set_option(key.encode(), None if value is None else str(value).encode()))
 
 

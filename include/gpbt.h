@@ -303,10 +303,13 @@ int gpbt_fanout_log_posterior_host(gpbt_fanout_t fanout, const double* X_host, d
                                    int max_devices, int* devices_used);
 
 /* Tuning overrides (tests, tuning tools).  The library reads GPBT_PC_TILE, GPBT_CHOL,
- * GPBT_LOWRANK_GENERIC, GPBT_NO_ZEROCOPY, GPBT_ENSEMBLE_SPLIT_KERNELS, GPBT_FANOUT_MIN_ROWS and
- * GPBT_CHOL_BATCH from the environment once, at load; this call changes one value afterwards.
+ * GPBT_LOWRANK_GENERIC, GPBT_NO_ZEROCOPY, GPBT_ENSEMBLE_SPLIT_KERNELS, GPBT_FANOUT_MIN_ROWS,
+ * GPBT_CHOL_BATCH, GPBT_CHOL_STREAMS and GPBT_CHOL_PIPE from the environment once, at load; this call
+ * changes one value afterwards.
  * keys: "pc_tile" (8|16|32), "chol" (warp|batch|staged|cta|fused), "lowrank_generic", "no_zerocopy",
- * "ensemble_split_kernels", "fanout_min_rows", "chol_batch", "cf_debug"; value NULL or "" restores the default. */
+ * "ensemble_split_kernels", "fanout_min_rows"; the fused Cholesky's schedule: "chol_batch" (walkers per
+ * sub-batch), "chol_streams", "chol_pipe" (kernel (a) pipelined over that many sub-batches), "chol_lag"
+ * (sub-batches start one step apart), "chol_prio", "cf_debug"; value NULL or "" restores the default. */
 int gpbt_set_option(const char* key, const char* value);
 
 /* bytes of device workspace the chain currently holds (grows with the largest N seen)        */
