@@ -492,17 +492,30 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
 
 
-def _event_ms(torch, fn, reps, warm=2):
+def _event_ms(torch, fn, reps, warm=2, per_call=True):
+    """CUDA-event time of one fn().  per_call: median over reps, one event pair per call (a host hiccup while a
+    call's 40-odd launches are being enqueued inflates that call only, not the figure); else the mean over reps
+    back-to-back calls between one event pair (single-kernel calls: the average launch duration)."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
+    if not per_call:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+    evs = []
     for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
         fn()
-    b.record()
+        b.record()
+        evs.append((a, b))
     torch.cuda.synchronize()
-    return a.elapsed_time(b) / reps
+    return float(np.median([a.elapsed_time(b) for a, b in evs]))
 
 
 def single_gpu_records(args, torch, dev, chain, states, sts, g, Xh, Xd, lp_check, world, W, K):
@@ -530,7 +543,7 @@ def single_gpu_records(args, torch, dev, chain, states, sts, g, Xh, Xd, lp_check
     def run_a():
         cnt[0] += 1
         return de.pc_predict_device(Xd[cnt[0] % nb])
-    ka_ms = _event_ms(torch, run_a, max(K, 10), warm=3)
+    ka_ms = _event_ms(torch, run_a, max(K, 10), warm=3, per_call=False)
     fl_a = flops_pc_predict(p, n, q)
 
     # ---- kernel (b) alone: covariance materialised, full 4096 walkers ---------------------------
